@@ -1,0 +1,252 @@
+// csrc/ccb_api.cu -- the extern "C" surface declared in include/ccb.h (handles, copies, launches).
+#include <cstring>
+#include <new>
+#include "ccb_internal.h"
+
+namespace ccb {
+const char* last_error_cstr();
+}
+using namespace ccb;
+
+extern "C" {
+
+const char* ccb_last_error(void) { return last_error_cstr(); }
+int ccb_version(void) { return 100; }
+int ccb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t ccb_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------------ mechanism
+int ccb_mech_create(const ccb_mech_desc* desc, ccb_mech** out) {
+    if (!out) { set_error("ccb_mech_create: out is NULL"); return CCB_E_INVALID; }
+    ccb_mech* m = new (std::nothrow) ccb_mech();
+    if (!m) { set_error("out of memory"); return CCB_E_INVALID; }
+    int rc = build_host_mech(desc, &m->h);
+    if (rc != CCB_OK) { delete m; return rc; }
+    *out = m;
+    return CCB_OK;
+}
+int ccb_mech_destroy(ccb_mech* m) {
+    if (!m) return CCB_OK;
+    free_dev_mech(&m->h);
+    delete m;
+    return CCB_OK;
+}
+int ccb_mech_dims(const ccb_mech* m, int32_t out[8]) {
+    if (!m || !out) { set_error("ccb_mech_dims: NULL"); return CCB_E_INVALID; }
+    out[0] = m->h.nb; out[1] = m->h.ne; out[2] = m->h.nj; out[3] = m->h.ml; out[4] = m->h.nnodes; out[5] = (int)m->h.loop_edges.size() / 2;
+    out[6] = 12 * m->h.nb; out[7] = m->h.lanes;
+    return CCB_OK;
+}
+static void copy_out(const std::vector<int>& v, int32_t* o) { if (o && !v.empty()) std::memcpy(o, v.data(), v.size() * sizeof(int)); }
+int ccb_mech_graph(const ccb_mech* m, int32_t* eqc_id, int32_t* body_id, int32_t* dfs_list, int32_t* parents, int32_t* loop_edges,
+                   int32_t* eqc_dim, int32_t* eqc_row0, int32_t* act_kind, int32_t* joint_elim) {
+    if (!m) { set_error("ccb_mech_graph: NULL"); return CCB_E_INVALID; }
+    copy_out(m->h.eqc_id, eqc_id); copy_out(m->h.body_id, body_id); copy_out(m->h.dfs_list, dfs_list); copy_out(m->h.parents, parents);
+    copy_out(m->h.loop_edges, loop_edges); copy_out(m->h.eqc_dim, eqc_dim); copy_out(m->h.eqc_row0, eqc_row0); copy_out(m->h.act_kind, act_kind);
+    copy_out(m->h.elim, joint_elim);
+    return CCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batch
+int ccb_batch_create(ccb_mech* m, int32_t B, int32_t device, ccb_batch** out) {
+    if (!m || !out || B < 1) { set_error("ccb_batch_create: bad arguments"); return CCB_E_INVALID; }
+    if (ccb_device_count() <= device || device < 0) { set_error("ccb_batch_create: no such CUDA device (this library has no CPU fallback)"); return CCB_E_CUDA; }
+    const DevMech* view;
+    int rc = get_dev_mech(&m->h, device, &view);
+    if (rc != CCB_OK) return rc;
+    ccb_batch* b = new ccb_batch();
+    b->mech = m; b->B = B; b->device = device;
+    CCB_CUDA(cudaSetDevice(device));
+    CCB_CUDA(cudaMalloc(&b->state, (size_t)B * m->h.nb * 13 * sizeof(double)));
+    CCB_CUDA(cudaMalloc(&b->lambda, (size_t)B * (m->h.ml > 0 ? m->h.ml : 1) * sizeof(double)));
+    CCB_CUDA(cudaMalloc(&b->status_dev, (size_t)B * sizeof(int)));
+    CCB_CUDA(cudaMemset(b->lambda, 0, (size_t)B * (m->h.ml > 0 ? m->h.ml : 1) * sizeof(double)));
+    CCB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    *out = b;
+    return CCB_OK;
+}
+int ccb_batch_destroy(ccb_batch* b) {
+    if (!b) return CCB_OK;
+    cudaSetDevice(b->device);
+    cudaFree(b->state); cudaFree(b->lambda); cudaFree(b->status_dev); cudaFree(b->storage_dev);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return CCB_OK;
+}
+int ccb_batch_set_state(ccb_batch* b, const double* state, const double* lambda) {
+    if (!b || !state) { set_error("ccb_batch_set_state: NULL"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(b->device));
+    const size_t ns = (size_t)b->B * b->mech->h.nb * 13 * sizeof(double), nl = (size_t)b->B * b->mech->h.ml * sizeof(double);
+    CCB_CUDA(cudaMemcpyAsync(b->state, state, ns, cudaMemcpyHostToDevice, b->stream));
+    if (nl) {
+        if (lambda) CCB_CUDA(cudaMemcpyAsync(b->lambda, lambda, nl, cudaMemcpyHostToDevice, b->stream));
+        else CCB_CUDA(cudaMemsetAsync(b->lambda, 0, nl, b->stream));
+    }
+    CCB_CUDA(cudaStreamSynchronize(b->stream));
+    return CCB_OK;
+}
+int ccb_batch_get_state(ccb_batch* b, double* state, double* lambda) {
+    if (!b) { set_error("ccb_batch_get_state: NULL"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(b->device));
+    const size_t ns = (size_t)b->B * b->mech->h.nb * 13 * sizeof(double), nl = (size_t)b->B * b->mech->h.ml * sizeof(double);
+    if (state) CCB_CUDA(cudaMemcpyAsync(state, b->state, ns, cudaMemcpyDeviceToHost, b->stream));
+    if (lambda && nl) CCB_CUDA(cudaMemcpyAsync(lambda, b->lambda, nl, cudaMemcpyDeviceToHost, b->stream));
+    CCB_CUDA(cudaStreamSynchronize(b->stream));
+    return CCB_OK;
+}
+int ccb_batch_device_ptrs(ccb_batch* b, void** state_dev, void** lambda_dev) {
+    if (!b) { set_error("ccb_batch_device_ptrs: NULL"); return CCB_E_INVALID; }
+    if (state_dev) *state_dev = b->state;
+    if (lambda_dev) *lambda_dev = b->lambda;
+    return CCB_OK;
+}
+int ccb_batch_sync(ccb_batch* b) {
+    if (!b) { set_error("ccb_batch_sync: NULL"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(b->device));
+    CCB_CUDA(cudaStreamSynchronize(b->stream));
+    return CCB_OK;
+}
+int ccb_batch_stream(ccb_batch* b, void** stream) {
+    if (!b || !stream) { set_error("ccb_batch_stream: NULL"); return CCB_E_INVALID; }
+    *stream = (void*)b->stream;
+    return CCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ controllers
+static int upload(ccb_ctrl* c, const void* host, size_t bytes, const void** dev) {
+    *dev = nullptr;
+    if (!host || bytes == 0) return CCB_OK;
+    void* p = nullptr;
+    CCB_CUDA(cudaMalloc(&p, bytes));
+    c->allocs.push_back(p);
+    CCB_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+    *dev = p;
+    return CCB_OK;
+}
+
+int ccb_ctrl_create(const ccb_mech* m, const ccb_ctrl_desc* d, int32_t device, ccb_ctrl** out) {
+    if (!m || !d || !out) { set_error("ccb_ctrl_create: NULL"); return CCB_E_INVALID; }
+    if (ccb_device_count() <= device || device < 0) { set_error("ccb_ctrl_create: no such CUDA device (this library has no CPU fallback)"); return CCB_E_CUDA; }
+    const HostMech& H = m->h;
+    const int nu = d->nu, n = 12 * H.nb, B = d->B > 0 ? d->B : 1;
+    if (d->kind < CCB_CTRL_NONE || d->kind > CCB_CTRL_PID) { set_error("ccb_ctrl_create: unknown kind"); return CCB_E_INVALID; }
+    if (d->kind != CCB_CTRL_NONE) {
+        if (nu < 1 || !d->eqc) { set_error("ccb_ctrl_create: no controlled eqcs"); return CCB_E_INVALID; }
+        for (int i = 0; i < nu; i++) {
+            int e = d->eqc[i];
+            // "Only 1 DOF joints are supported" (reference src/control/pid.jl:20,36; lqr.jl K is 1 x NK per eqc)
+            if (e < 0 || e >= H.ne || H.act_kind[e] == 0) { set_error("ccb_ctrl_create: Only 1 DOF joints are supported"); return CCB_E_INVALID; }
+        }
+    }
+    if ((d->kind == CCB_CTRL_LQR_FIN || d->kind == CCB_CTRL_TRACKING) && d->N < 2) { set_error("ccb_ctrl_create: horizon N must be >= 2"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(device));
+    ccb_ctrl* c = new ccb_ctrl();
+    c->device = device; c->B = B;
+    std::memset(&c->v, 0, sizeof(c->v));
+    c->v.kind = d->kind; c->v.nu = nu; c->v.N = d->N;
+    auto mult = [&](int64_t bs) { return bs == 0 ? (size_t)1 : (size_t)B; };
+    int rc = CCB_OK;
+    const void* p;
+    auto fail = [&](int r) { ccb_ctrl_destroy(c); return r; };
+    if (d->kind != CCB_CTRL_NONE) { if ((rc = upload(c, d->eqc, nu * sizeof(int), &p))) return fail(rc); c->v.eqc = (const int*)p; }
+    if (d->kind == CCB_CTRL_LQR_INF || d->kind == CCB_CTRL_LQR_FIN || d->kind == CCB_CTRL_TRACKING) {
+        if (!d->K || !d->zd || !d->Fd) { set_error("ccb_ctrl_create: K, zd and Fd are required"); return fail(CCB_E_INVALID); }
+        const size_t rows = d->kind == CCB_CTRL_LQR_INF ? 1 : (size_t)d->N - 1;
+        const size_t nz = d->kind == CCB_CTRL_TRACKING ? (size_t)d->N : 1;
+        if ((rc = upload(c, d->K, mult(d->K_bstride) * rows * nu * n * sizeof(double), &p))) return fail(rc);
+        c->v.K = (const double*)p; c->v.K_bs = d->K_bstride;
+        if ((rc = upload(c, d->zd, mult(d->zd_bstride) * nz * H.nb * 13 * sizeof(double), &p))) return fail(rc);
+        c->v.zd = (const double*)p; c->v.zd_bs = d->zd_bstride;
+        if ((rc = upload(c, d->Fd, mult(d->Fd_bstride) * nz * nu * sizeof(double), &p))) return fail(rc);
+        c->v.Fd = (const double*)p; c->v.Fd_bs = d->Fd_bstride;
+    } else if (d->kind == CCB_CTRL_TABLE) {
+        if (!d->U || d->N < 1) { set_error("ccb_ctrl_create: U[N][nu] is required"); return fail(CCB_E_INVALID); }
+        if ((rc = upload(c, d->U, mult(d->U_bstride) * (size_t)d->N * nu * sizeof(double), &p))) return fail(rc);
+        c->v.U = (const double*)p; c->v.U_bs = d->U_bstride;
+    } else if (d->kind == CCB_CTRL_PID) {
+        if (!d->P || !d->I || !d->D || !d->goal) { set_error("ccb_ctrl_create: P, I, D, goal are required"); return fail(CCB_E_INVALID); }
+        if ((rc = upload(c, d->P, nu * sizeof(double), &p))) return fail(rc); c->v.P = (const double*)p;
+        if ((rc = upload(c, d->I, nu * sizeof(double), &p))) return fail(rc); c->v.I = (const double*)p;
+        if ((rc = upload(c, d->D, nu * sizeof(double), &p))) return fail(rc); c->v.D = (const double*)p;
+        if ((rc = upload(c, d->goal, mult(d->goal_bstride) * nu * sizeof(double), &p))) return fail(rc);
+        c->v.goal = (const double*)p; c->v.goal_bs = d->goal_bstride;
+        void* q = nullptr;
+        CCB_CUDA(cudaMalloc(&q, (size_t)B * nu * sizeof(double))); c->allocs.push_back(q); c->v.pid_int = (double*)q;
+        CCB_CUDA(cudaMemset(q, 0, (size_t)B * nu * sizeof(double)));
+        CCB_CUDA(cudaMalloc(&q, (size_t)B * nu * sizeof(double))); c->allocs.push_back(q); c->v.pid_last = (double*)q;
+        CCB_CUDA(cudaMemset(q, 0, (size_t)B * nu * sizeof(double)));
+    }
+    *out = c;
+    return CCB_OK;
+}
+int ccb_ctrl_destroy(ccb_ctrl* c) {
+    if (!c) return CCB_OK;
+    cudaSetDevice(c->device);
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+    return CCB_OK;
+}
+int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t set) {
+    if (!c || c->v.kind != CCB_CTRL_PID) { set_error("ccb_ctrl_pid_state: not a PID controller"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->B * c->v.nu * sizeof(double);
+    if (set) {
+        if (integrated) CCB_CUDA(cudaMemcpy(c->v.pid_int, integrated, bytes, cudaMemcpyHostToDevice));
+        if (last) CCB_CUDA(cudaMemcpy(c->v.pid_last, last, bytes, cudaMemcpyHostToDevice));
+    } else {
+        if (integrated) CCB_CUDA(cudaMemcpy(integrated, c->v.pid_int, bytes, cudaMemcpyDeviceToHost));
+        if (last) CCB_CUDA(cudaMemcpy(last, c->v.pid_last, bytes, cudaMemcpyDeviceToHost));
+    }
+    return CCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ simulate!
+int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage_dev,
+                        int32_t* status_dev) {
+    if (!b || steps < 0) { set_error("ccb_simulate: bad arguments"); return CCB_E_INVALID; }
+    if (ctrl && ctrl->device != b->device) { set_error("ccb_simulate: controller lives on another device"); return CCB_E_INVALID; }
+    if (ctrl && ctrl->B != b->B && ctrl->B != 1) { set_error("ccb_simulate: controller tables were laid out for another batch size"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(b->device));
+    const DevMech* view;
+    int rc = get_dev_mech(&b->mech->h, b->device, &view);
+    if (rc != CCB_OK) return rc;
+    DevCtrl C;
+    std::memset(&C, 0, sizeof(C));
+    if (ctrl) C = ctrl->v;
+    SimArgs a;
+    a.state = b->state; a.lambda = b->lambda; a.storage = storage_dev; a.status = status_dev;
+    a.B = b->B; a.k0 = k0; a.steps = steps;
+    a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
+    a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
+    a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;
+    int lanes = opts && opts->lanes > 0 ? opts->lanes : b->mech->h.lanes;
+    return launch_rollout(*view, C, a, lanes, b->stream);
+}
+
+int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage, int32_t* status) {
+    if (!b) { set_error("ccb_simulate: NULL batch"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(b->device));
+    const size_t per_step = (size_t)b->B * b->mech->h.nb * 13;
+    double* sdev = nullptr;
+    if (storage && steps > 0) {
+        const size_t need = per_step * steps * sizeof(double);
+        if (b->storage_cap < need) {
+            cudaFree(b->storage_dev); b->storage_dev = nullptr; b->storage_cap = 0;
+            CCB_CUDA(cudaMalloc(&b->storage_dev, need));
+            b->storage_cap = need;
+        }
+        sdev = b->storage_dev;
+    }
+    int rc = ccb_simulate_device(b, ctrl, k0, steps, opts, sdev, b->status_dev);
+    if (rc != CCB_OK) return rc;
+    if (sdev) CCB_CUDA(cudaMemcpyAsync(storage, sdev, per_step * steps * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (status) CCB_CUDA(cudaMemcpyAsync(status, b->status_dev, (size_t)b->B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CCB_CUDA(cudaStreamSynchronize(b->stream));
+    return CCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+"""shared helpers for the parity tests (oracle = checker only)"""
+import math
+
+import numpy as np
+
+
+def zd_of(mech, cfg):
+    zd = np.zeros((mech.nb, 13))
+    zd[:, 3] = 1.0
+    if cfg.get("xd") is not None:
+        zd[:, 0:3] = np.array(cfg["xd"])
+    if cfg.get("qd") is not None:
+        zd[:, 3:7] = np.array(cfg["qd"])
+    return zd
+
+
+def oracle_lqr_gains(cc, orc, mech, cfg, horizon=None):
+    """LQR constructor logic (lqr.jl:17-47) evaluated with the oracle: returns K [rows][nu][n], N, zd, Fd, eqc_idx"""
+    om = orc.OracleMech(mech.desc())
+    zd = zd_of(mech, cfg)
+    eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    Fd = np.array(cfg.get("Ftaud", np.zeros(len(eqc_idx))), dtype=float)
+    lin = om.linearize(zd, Fd, eqc_idx)
+    Q = cc.blockdiag(cfg["Q"]) * mech.dt
+    R = cc.blockdiag(cfg["R"]) * mech.dt
+    horizon = cfg["horizon"] if horizon is None else horizon
+    if horizon == math.inf:
+        N, Ntemp = math.inf, int(math.ceil(10 / mech.dt))
+    else:
+        N = Ntemp = int(math.ceil(horizon / mech.dt))
+    res = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Q, R, Ntemp)
+    K = res["Ku"][:1] if N == math.inf else res["Ku"]
+    return dict(K=K, N=N, zd=zd, Fd=Fd, eqc_idx=eqc_idx, om=om, lin=lin, res=res)
+
+
+def rel_err(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def cartpole_states(cc, mech, B, seed=1, ymax=0.5, phimax=0.2):
+    """y0 ~ U(-0.5,0.5), theta0 ~ U(-0.2,0.2), zero velocity"""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((B, mech.nb, 13))
+    for s in range(B):
+        cc.examples.set_cartpole_pose(mech, rng.uniform(-ymax, ymax), rng.uniform(-phimax, phimax, size=mech.nb - 1))
+        out[s] = mech.state_vector()
+    return out
