@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: closed-loop sim steps/s of the batched LQR cartpole rollout
+(BASELINE.json configs[1]: lqr_cartpole, batch of 4096 random initial states, 2000-step closed-loop rollout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One bench "step" = one pass of the hot path over one batch = 4096 systems x 2000 simulate! steps in ONE launch of
+the fused rollout kernel.  Prints one JSON line (see the contract in the task statement):
+  value     whole-job sim steps/s with the batch already resident in HBM (CUDA events on the launching stream)
+  e2e       the same metric through the public API with HOST buffers (pinned H2D of the initial states and D2H of
+            the final states + status inside the timed region)
+  roofline  algorithmic HBM bytes (2*8*(13 Nb + m_lambda) per system-step) / kernel time vs the
+            measured HBM peak -- this kernel is FP64-issue/latency bound, not HBM bound, and says so
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on all host cores, bounded sample
+Multi-GPU (torchrun): one process per GPU, the batch is sharded by replication of the per-GPU batch (weak
+scaling), no data-path collective; time = max over ranks.
+`--impl reference` times the CPU restatement of the reference on the host cores (the Julia reference cannot run
+here: no julia toolchain).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 4096
+SIM_STEPS = 2000
+WORKLOAD = "lqr_cartpole batch=4096 random initial states, 2000-step closed-loop rollout (finite-horizon LQR, horizon 20 s)"
+
+
+def cartpole_problem(cc, B, seed=1):
+    """SURVEY 8(d) C2 inputs: y0 ~ U(-0.5,0.5), theta0 ~ U(-0.2,0.2), zero velocity (numpy default_rng(seed))"""
+    mech, cfg = cc.examples.cartpole()
+    rng = np.random.default_rng(seed)
+    st = np.zeros((B, mech.nb, 13))
+    for s in range(B):
+        cc.examples.set_cartpole_pose(mech, rng.uniform(-0.5, 0.5), rng.uniform(-0.2, 0.2, size=1))
+        st[s] = mech.state_vector()
+    return mech, cfg, st
+
+
+def alg_bytes_per_system_step(mech):
+    return 2 * 8 * (13 * mech.nb + mech.ml)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)"""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([p.strip() for p in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def oracle_gains(cc, orc, mech, cfg, horizon):
+    """finite-horizon LQR gains for the workload (synthesised once, outside every timed region)"""
+    om = orc.OracleMech(mech.desc())
+    zd = np.zeros((mech.nb, 13)); zd[:, 3] = 1.0
+    zd[:, 0:3] = np.array(cfg["xd"])
+    eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    lin = om.linearize(zd, np.zeros(len(eqc_idx)), eqc_idx)
+    N = int(math.ceil(horizon / mech.dt))
+    res = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], cc.blockdiag(cfg["Q"]) * mech.dt, cc.blockdiag(cfg["R"]) * mech.dt, N)
+    return om, res["Ku"], N, zd, eqc_idx
+
+
+def gains_for(cc, mech, cfg, horizon):
+    """gain table through the product's own GPU synthesis when it is available, else from the checker"""
+    try:
+        lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], horizon, xd=cfg["xd"])
+        return lqr, "gpu"
+    except cc.CcbError:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        _, K, N, zd, _ = oracle_gains(cc, orc, mech, cfg, horizon)
+        return cc.LQR.from_gains(mech, cfg["eqcids"], K, N, xd=cfg["xd"]), "oracle"
+
+
+def cpu_reference_run(steps, warmup, sample_systems=None):
+    """the reference arm / cpu_baseline: CPU restatement on all host cores, bounded sample of the same workload"""
+    import ccb200 as cc
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    mech, cfg, st = cartpole_problem(cc, BATCH)
+    om, K, N, zd, eqc_idx = oracle_gains(cc, orc, mech, cfg, 20.0)
+    # calibrate, then size one "step" to about 4 s of CPU work
+    nb = min(BATCH, 4 * cores)
+    ctrl = om.make_ctrl(nb, kind="lqr_finite", eqc=eqc_idx, N=N, K=K, zd=zd, Fd=np.zeros(len(eqc_idx)))
+    t0 = time.time()
+    om.simulate(st[:nb], 100, ctrl=ctrl, nthreads=cores)
+    rate = nb * 100 / (time.time() - t0)
+    if sample_systems is None:
+        sample_systems = int(min(BATCH, max(cores, rate * 4.0 / SIM_STEPS)))
+        sample_systems = max(cores, (sample_systems // cores) * cores)
+    ctrl = om.make_ctrl(sample_systems, kind="lqr_finite", eqc=eqc_idx, N=N, K=K, zd=zd, Fd=np.zeros(len(eqc_idx)))
+    for _ in range(warmup):
+        om.simulate(st[:sample_systems], 50, ctrl=ctrl, nthreads=cores)
+    t0 = time.time()
+    for _ in range(steps):
+        om.simulate(st[:sample_systems], SIM_STEPS, ctrl=ctrl, nthreads=cores)
+    dt = time.time() - t0
+    value = sample_systems * SIM_STEPS * steps / dt
+    sample = f"{sample_systems} of {BATCH} systems x {SIM_STEPS} sim steps per bench step, {cores} std::threads"
+    return value, cores, sample, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, cores, sample, ms = cpu_reference_run(K, W)
+        print(json.dumps({
+            "impl": "reference", "metric": "closed-loop sim steps/s", "value": value, "unit": "sim steps/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference algorithm (Julia reference not runnable here)"},
+            "cpu_baseline": {"value": value, "unit": "sim steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "sim steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import ccb200 as cc
+    if not torch.cuda.is_available() or cc.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    dev = local_rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    mech, cfg, st0 = cartpole_problem(cc, BATCH, seed=1 + rank)
+    lqr, gain_src = gains_for(cc, mech, cfg, 20.0)
+    batch = cc.Batch(mech, BATCH, dev)
+    stream = torch.cuda.ExternalStream(batch.stream(), device=dev)
+    nst = mech.nb * 13
+    host_in = torch.from_numpy(st0.reshape(BATCH, nst)).pin_memory()
+    host_out = torch.empty((BATCH, nst), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{dev}")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def kernel_step(timed):
+        batch.set_state(host_in.numpy())                      # reset the batch (outside the timed region)
+        flush.fill_(rank & 0xFF)                              # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        batch.simulate_device(lqr, 1, SIM_STEPS, lanes=args.lanes)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(W):
+        kernel_step(False)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    barrier()
+    launches0 = cc._lib.lib().ccb_launch_count()
+    t_wall0 = time.time()
+    times = [kernel_step(True) for _ in range(K)]
+    barrier()
+    wall = time.time() - t_wall0
+    launches = int(cc._lib.lib().ccb_launch_count() - launches0)
+    kernel_ms = float(sum(times))
+    final_dev = batch.get_state()
+
+    # end-to-end through the public API (host buffers; H2D + kernel + D2H inside the timed region)
+    def e2e_step():
+        batch.set_state(host_in.numpy())
+        _, status = batch.simulate(lqr, 1, SIM_STEPS, lanes=args.lanes)
+        out = batch.get_state()
+        host_out.numpy()[...] = out.reshape(BATCH, nst)
+        return status
+
+    for _ in range(min(W, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.time()
+    for _ in range(K):
+        status = e2e_step()
+    barrier()
+    e2e_s = time.time() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert np.all(status > 0), "a Newton solve failed inside the bench"
+    assert np.allclose(host_out.numpy().reshape(final_dev.shape), final_dev, rtol=0, atol=0), "e2e and device-resident runs disagree"
+
+    # max over ranks
+    t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_s = float(t[0]), float(t[1])
+    units = world * BATCH * SIM_STEPS * K
+    value = units / (kernel_ms * 1e-3)
+    e2e_value = units / e2e_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        per_launch_s = kernel_ms * 1e-3 / K
+        alg_bytes = alg_bytes_per_system_step(mech) * BATCH * SIM_STEPS
+        achieved = alg_bytes / per_launch_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        out = {
+            "metric": "closed-loop sim steps/s", "value": value, "unit": "sim steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": kernel_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sim_steps": SIM_STEPS, "mechanism": "cartpole (2 bodies, 2 joints, m_lambda=10)",
+                       "newton_eps": 1e-10, "gains": gain_src, "l2": "flushed (256 MB write) between timed iterations",
+                       "parallelism": f"dp{world} (independent systems, no collective on the step path)",
+                       "lanes_per_system": args.lanes or cc.handle(mech).lanes},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src,
+                         "note": "algorithmic bytes = 2*8*(13*Nb+m_lambda) per system-step (SURVEY 8(d)); the fused kernel keeps state on chip, "
+                                 "so it is FP64 issue/latency bound, not HBM bound"},
+            "e2e": {"value": e2e_value, "unit": "sim steps/s", "h2d_bytes_per_step": int(BATCH * nst * 8), "d2h_bytes_per_step": int(BATCH * nst * 8 + BATCH * 4)},
+            "gpu_launches": launches, "clocks": sampler.summary(), "wall_s_timed_region": wall,
+            "newton_iters_per_sim_step": float(status.mean() / SIM_STEPS),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_reference_run(1, 0)
+            out["cpu_baseline"] = {"value": v, "unit": "sim steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

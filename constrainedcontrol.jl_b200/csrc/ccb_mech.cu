@@ -196,7 +196,7 @@ int build_host_mech(const ccb_mech_desc* d, HostMech* M) {
     }
     // default lanes per system: enough for one pass over the constraint rows, at most a warp
     int want = std::max(M->ml, 2 * nb);
-    M->lanes = want <= 4 ? 4 : want <= 8 ? 8 : want <= 16 ? 16 : 32;
+    M->lanes = want <= 12 ? 8 : want <= 24 ? 16 : 32;   // measured: fewer lanes per system win (issue-bound)
     return CCB_OK;
 }
 

@@ -146,57 +146,92 @@ __device__ __forceinline__ double eval_system(const DevMech& M, const SysMem& m,
     return ss;
 }
 
+// Elimination of one joint block of compile-time size DC.  Every lane factorises S_cc redundantly in registers (LU
+// without pivoting: S_cc is the Schur complement of a quasi-definite KKT matrix) and applies the solve to the column(s)
+// it owns of [S_c,later | rhs_c]; afterwards lanes own (row, column) items of the later neighbours' Schur update.
+template <int G, int DC>
+__device__ __forceinline__ void eliminate_block(const DevMech& M, const SysMem& m, int c, int lane, bool active) {
+    const int r0 = __ldg(M.j_row0 + c), ncol = __ldg(M.j_ncol + c);
+    const int a0 = __ldg(M.acol_ptr + c), nac = __ldg(M.acol_ptr + c + 1) - a0;
+    double* Sc = m.S + __ldg(M.j_soff + c);
+    if (active && lane <= nac) {
+        double A[DC][DC], invd[DC];
+#pragma unroll
+        for (int i = 0; i < DC; i++)
+#pragma unroll
+            for (int j = 0; j < DC; j++) A[i][j] = Sc[i * ncol + j];
+#pragma unroll
+        for (int k = 0; k < DC; k++) {
+            invd[k] = 1.0 / A[k][k];
+#pragma unroll
+            for (int i = k + 1; i < DC; i++) {
+                A[i][k] *= invd[k];
+#pragma unroll
+                for (int j = k + 1; j < DC; j++) A[i][j] = fma(-A[i][k], A[k][j], A[i][j]);
+            }
+        }
+        for (int t = lane; t <= nac; t += G) {
+            double x[DC];
+            const int cc = (t < nac) ? __ldg(M.acol + a0 + t) : 0;
+#pragma unroll
+            for (int i = 0; i < DC; i++) x[i] = (t < nac) ? Sc[i * ncol + cc] : m.rhs[r0 + i];
+#pragma unroll
+            for (int k = 0; k < DC; k++)
+#pragma unroll
+                for (int i = k + 1; i < DC; i++) x[i] = fma(-A[i][k], x[k], x[i]);
+#pragma unroll
+            for (int k = DC - 1; k >= 0; k--) {
+#pragma unroll
+                for (int j = k + 1; j < DC; j++) x[k] = fma(-A[k][j], x[j], x[k]);
+                x[k] *= invd[k];
+            }
+#pragma unroll
+            for (int i = 0; i < DC; i++) {
+                if (t < nac) Sc[i * ncol + cc] = x[i];
+                else m.rhs[r0 + i] = x[i];
+            }
+        }
+    }
+    __syncwarp();
+    // Schur update of every later neighbour p:  S_p,* -= S_pc U_c,* ; rhs_p -= S_pc y_c
+    for (int e = __ldg(M.lat_ptr + c); e < __ldg(M.lat_ptr + c + 1); e++) {
+        const int p = __ldg(M.lat_p + e), pc0 = __ldg(M.lat_pc0 + e), mo = __ldg(M.lat_map + e);
+        const int dp = __ldg(M.j_dim + p), ncp = __ldg(M.j_ncol + p), rp0 = __ldg(M.j_row0 + p);
+        double* Sp = m.S + __ldg(M.j_soff + p);
+        const int items = dp * (nac + 1);
+        if (active) {
+            for (int it = lane; it < items; it += G) {
+                const int row = it / (nac + 1), i = it - row * (nac + 1);
+                const double* t = Sp + row * ncp + pc0;
+                double acc = 0.0;
+                if (i < nac) {
+                    const int cc = __ldg(M.acol + a0 + i);
+#pragma unroll
+                    for (int k = 0; k < DC; k++) acc = fma(t[k], Sc[k * ncol + cc], acc);
+                    Sp[row * ncp + __ldg(M.map + mo + i)] -= acc;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DC; k++) acc = fma(t[k], m.rhs[r0 + k], acc);
+                    m.rhs[rp0 + row] -= acc;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Solve S dλ = rhs by the leaf-first block sweep (rhs carried along), back-substitute, then recover the body steps
 // ds_b = D_b^-1 (d_b + G_b^T dλ).  On exit m.rhs holds dλ and m.ds holds ds.
 template <int G> __device__ __forceinline__ void solve_system(const DevMech& M, const SysMem& m, int lane, bool active) {
     for (int idx = 0; idx < M.nj; idx++) {
         const int c = __ldg(M.elim + idx);
-        const int dc = __ldg(M.j_dim + c), r0 = __ldg(M.j_row0 + c), ncol = __ldg(M.j_ncol + c);
-        const int a0 = __ldg(M.acol_ptr + c), nac = __ldg(M.acol_ptr + c + 1) - a0;
-        double* Sc = m.S + __ldg(M.j_soff + c);
-        // Gauss-Jordan on the diagonal block, row-distributed: the block becomes I, the active columns U = S_cc^-1 S_c,later
-        for (int k = 0; k < dc; k++) {
-            if (active && lane == k) {
-                double* row = Sc + k * ncol;
-                const double inv = 1.0 / row[k];
-                for (int t = k + 1; t < dc; t++) row[t] *= inv;
-                for (int t = 0; t < nac; t++) row[__ldg(M.acol + a0 + t)] *= inv;
-                m.rhs[r0 + k] *= inv;
-            }
-            __syncwarp();
-            if (active && lane < dc && lane != k) {
-                double* row = Sc + lane * ncol;
-                const double* prow = Sc + k * ncol;
-                const double f = row[k];
-                for (int t = k + 1; t < dc; t++) row[t] = fma(-f, prow[t], row[t]);
-                for (int t = 0; t < nac; t++) { const int cc = __ldg(M.acol + a0 + t); row[cc] = fma(-f, prow[cc], row[cc]); }
-                m.rhs[r0 + lane] = fma(-f, m.rhs[r0 + k], m.rhs[r0 + lane]);
-            }
-            __syncwarp();
-        }
-        // Schur update of every later neighbour p:  S_p,* -= S_pc U_c,* ; rhs_p -= S_pc y_c
-        for (int e = __ldg(M.lat_ptr + c); e < __ldg(M.lat_ptr + c + 1); e++) {
-            const int p = __ldg(M.lat_p + e), pc0 = __ldg(M.lat_pc0 + e), mo = __ldg(M.lat_map + e);
-            const int dp = __ldg(M.j_dim + p), ncp = __ldg(M.j_ncol + p), rp0 = __ldg(M.j_row0 + p);
-            double* Sp = m.S + __ldg(M.j_soff + p);
-            const int items = dp * (nac + 1);
-            if (active) {
-                for (int it = lane; it < items; it += G) {
-                    const int row = it / (nac + 1), i = it - row * (nac + 1);
-                    const double* t = Sp + row * ncp + pc0;
-                    if (i < nac) {
-                        const int cc = __ldg(M.acol + a0 + i);
-                        double acc = 0.0;
-                        for (int k = 0; k < dc; k++) acc = fma(t[k], Sc[k * ncol + cc], acc);
-                        Sp[row * ncp + __ldg(M.map + mo + i)] -= acc;
-                    } else {
-                        double acc = 0.0;
-                        for (int k = 0; k < dc; k++) acc = fma(t[k], m.rhs[r0 + k], acc);
-                        m.rhs[rp0 + row] -= acc;
-                    }
-                }
-            }
-            __syncwarp();
+        switch (__ldg(M.j_dim + c)) {
+            case 1: eliminate_block<G, 1>(M, m, c, lane, active); break;
+            case 2: eliminate_block<G, 2>(M, m, c, lane, active); break;
+            case 3: eliminate_block<G, 3>(M, m, c, lane, active); break;
+            case 4: eliminate_block<G, 4>(M, m, c, lane, active); break;
+            case 5: eliminate_block<G, 5>(M, m, c, lane, active); break;
+            default: eliminate_block<G, 6>(M, m, c, lane, active); break;
         }
     }
     // back substitution, root first
