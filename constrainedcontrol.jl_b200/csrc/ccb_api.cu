@@ -219,7 +219,7 @@ int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps,
     if (ctrl) C = ctrl->v;
     SimArgs a;
     a.state = b->state; a.lambda = b->lambda; a.storage = storage_dev; a.status = status_dev;
-    a.B = b->B; a.k0 = k0; a.steps = steps;
+    a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr;
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
     a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;

@@ -64,6 +64,12 @@ struct DevMech {
     const int* lat_pc0;        //   column position of c's block inside p's rows
     const int* lat_map;        //   offset into map[]: for each active column i of c, its position inside p's rows
     const int* map;
+    // body -> incident joints, and body -> coupled bodies (self first): block-sparsity of the linearisation
+    const int* bj_ptr;         // [nb+1]
+    const int* bj_joint;
+    const int* bj_side;
+    const int* cb_ptr;         // [nb+1]
+    const int* cb_body;
     // actuation (1-DoF eqcs)
     const int* eqc_act_joint;  // [ne] or -1
     const int* eqc_act_kind;   // [ne] 0 none, 1 force, 2 torque
@@ -84,7 +90,7 @@ struct HostMech {
     std::vector<int> eqc_id, body_id, dfs_list, parents, loop_edges;
     // joint-level plan
     std::vector<int> elim, j_soff, j_ncol, j_self, nbr_ptr, nbr_joint, nbr_cpos, nbr_pairs, acol_ptr, acol, acol_row, lat_ptr, lat_p, lat_pc0, lat_map,
-        map, binc_ptr, binc_row, binc_side;
+        map, binc_ptr, binc_row, binc_side, bj_ptr, bj_joint, bj_side, cb_ptr, cb_body;
     int S_doubles = 0;
     int lanes = 8;   // default lanes per system
     // per-device uploads
@@ -117,10 +123,13 @@ struct SimArgs {
     int B, k0, steps;
     double eps;
     int newton_iter, line_iter;
+    int knot_input;     // 1: `state` already holds the knot (x2,q2,v1,w1) of a setpoint; one Newton solve, state untouched (linearsystem)
+    double* s_out;      // [B][nb][6] solution (v2,w2) when knot_input
 };
 
 int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, cudaStream_t stream);
 int rollout_smem_bytes(const DevMech& M, int lanes);
+int default_lanes(const HostMech& h);
 
 }  // namespace ccb
 

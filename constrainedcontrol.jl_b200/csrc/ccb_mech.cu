@@ -194,6 +194,22 @@ int build_host_mech(const ccb_mech_desc* d, HostMech* M) {
         }
         M->binc_ptr[b + 1] = (int)M->binc_row.size();
     }
+    // joints incident to each body and the bodies it is coupled to through them
+    M->bj_ptr.assign(nb + 1, 0); M->cb_ptr.assign(nb + 1, 0);
+    for (int b = 0; b < nb; b++) {
+        std::vector<int> cb = {b};
+        for (int j = 0; j < nj; j++) {
+            int side = M->j_parent[j] == b ? 0 : (M->j_child[j] == b ? 1 : -1);
+            if (side < 0) continue;
+            M->bj_joint.push_back(j); M->bj_side.push_back(side);
+            int other = side == 0 ? M->j_child[j] : M->j_parent[j];
+            if (other >= 0 && std::find(cb.begin(), cb.end(), other) == cb.end()) cb.push_back(other);
+        }
+        M->bj_ptr[b + 1] = (int)M->bj_joint.size();
+        std::sort(cb.begin() + 1, cb.end());
+        M->cb_body.insert(M->cb_body.end(), cb.begin(), cb.end());
+        M->cb_ptr[b + 1] = (int)M->cb_body.size();
+    }
     // default lanes per system: enough for one pass over the constraint rows, at most a warp
     int want = std::max(M->ml, 2 * nb);
     M->lanes = want <= 12 ? 8 : want <= 24 ? 16 : 32;   // measured: fewer lanes per system win (issue-bound)
@@ -213,7 +229,8 @@ int get_dev_mech(HostMech* M, int device, const DevMech** view) {
            o_soff = addi(M->j_soff), o_ncol = addi(M->j_ncol), o_self = addi(M->j_self), o_nbp = addi(M->nbr_ptr), o_nbj = addi(M->nbr_joint),
            o_nbc = addi(M->nbr_cpos), o_nbm = addi(M->nbr_pairs), o_elim = addi(M->elim), o_acp = addi(M->acol_ptr), o_ac = addi(M->acol), o_acr = addi(M->acol_row),
            o_lp = addi(M->lat_ptr), o_lpp = addi(M->lat_p), o_lpc = addi(M->lat_pc0), o_lm = addi(M->lat_map), o_map = addi(M->map),
-           o_aj = addi(M->act_joint), o_ak = addi(M->act_kind);
+           o_aj = addi(M->act_joint), o_ak = addi(M->act_kind), o_bjp = addi(M->bj_ptr), o_bjj = addi(M->bj_joint), o_bjs = addi(M->bj_side),
+           o_cbp = addi(M->cb_ptr), o_cbb = addi(M->cb_body);
     size_t o_mass = addd(M->mass), o_in = addd(M->inertia), o_rp = addd(M->row_proj), o_p1 = addd(M->j_p1), o_p2 = addd(M->j_p2),
            o_qo = addd(M->j_qoff), o_ax = addd(M->j_axis);
     HostMech::Upload up;
@@ -231,6 +248,7 @@ int get_dev_mech(HostMech* M, int device, const DevMech** view) {
     v.nbr_ptr = I + o_nbp; v.nbr_joint = I + o_nbj; v.nbr_cpos = I + o_nbc; v.nbr_pairs = I + o_nbm; v.elim = I + o_elim; v.acol_ptr = I + o_acp;
     v.acol = I + o_ac; v.acol_row = I + o_acr; v.lat_ptr = I + o_lp; v.lat_p = I + o_lpp; v.lat_pc0 = I + o_lpc; v.lat_map = I + o_lm; v.map = I + o_map;
     v.eqc_act_joint = I + o_aj; v.eqc_act_kind = I + o_ak;
+    v.bj_ptr = I + o_bjp; v.bj_joint = I + o_bjj; v.bj_side = I + o_bjs; v.cb_ptr = I + o_cbp; v.cb_body = I + o_cbb;
     // shared-memory layout of one system
     int o = 0;
     const int nb = M->nb, ml = M->ml;

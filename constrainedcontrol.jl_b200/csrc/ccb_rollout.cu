@@ -417,9 +417,11 @@ template <int G> __global__ void __launch_bounds__(32) rollout_kernel(const DevM
             for (int b = lane; b < M.nb; b += G) {
                 double* zb = m.z + 13 * b;
                 V3 v = ld3(zb + 7), w = ld3(zb + 10);
-                st3(zb, ld3(zb) + dt * v);
-                double sq = sqrt(c4 - dot(w, w));
-                st4(zb + 3, qmul(ld4(zb + 3), Q4{0.5 * dt * sq, 0.5 * dt * w.x, 0.5 * dt * w.y, 0.5 * dt * w.z}));
+                if (!A.knot_input) {
+                    st3(zb, ld3(zb) + dt * v);
+                    double sq = sqrt(c4 - dot(w, w));
+                    st4(zb + 3, qmul(ld4(zb + 3), Q4{0.5 * dt * sq, 0.5 * dt * w.x, 0.5 * dt * w.y, 0.5 * dt * w.z}));
+                }
                 for (int i = 0; i < 6; i++) m.s[6 * b + i] = zb[7 + i];   // Newton starts from (v1, w1)
             }
         }
@@ -499,7 +501,11 @@ template <int G> __global__ void __launch_bounds__(32) rollout_kernel(const DevM
         }
         __syncwarp();
     }
-    if (valid) {
+    if (valid && A.knot_input) {
+        for (int i = lane; i < 6 * M.nb; i += G) A.s_out[(size_t)sys * 6 * M.nb + i] = m.s[i];
+        for (int i = lane; i < M.ml; i += G) A.lambda[(size_t)sys * M.ml + i] = m.lam[i];
+        if (A.status && lane == 0) A.status[sys] = failed ? -total_iters : total_iters;
+    } else if (valid) {
         for (int i = lane; i < nst; i += G) A.state[(size_t)sys * nst + i] = m.z[i];
         for (int i = lane; i < M.ml; i += G) A.lambda[(size_t)sys * M.ml + i] = m.lam[i];
         if (A.status && lane == 0) A.status[sys] = failed ? -total_iters : total_iters;

@@ -1,27 +1,188 @@
-// csrc/ccb_synth.cu -- linearsystem / dlqr / LQR + TrackingLQR synthesis entry points (K2, K3/K4)
+// csrc/ccb_synth.cu -- C-ABI entry points for linearsystem / dlqr / LQR and TrackingLQR gain synthesis (K2 + K3).
+#include <algorithm>
+#include <cstring>
+#include <vector>
 #include "ccb_internal.h"
+
+namespace ccb {
+int linearize_device(HostMech* H, int device, int S, double* d_zd, const double* d_Fd, const int* d_eqc, int nu, const ccb_sim_opts* opts,
+                     double* d_A, double* d_Bu, double* d_Bl, double* d_G, double* d_lam, double* d_s, int* d_status, cudaStream_t stream);
+size_t riccati_project_ws_doubles(int n, int nu, int ml);
+size_t riccati_sweep_ws_doubles(int n, int nu);
+int riccati_project_device(int P, int n, int nu, int ml, const double* A, const double* Bu, const double* Bl, const double* G, double* At, double* D,
+                           double* ws, cudaStream_t stream);
+int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
+                         long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
+                         int* kexit, int* iters, double* ws, cudaStream_t stream);
+}
 using namespace ccb;
+
+namespace {
+
+// tiny RAII pool of device allocations for one API call
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> int get(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+        ptrs.push_back(p);
+        *out = (T*)p;
+        return CCB_OK;
+    }
+    template <class T> int put(T** out, const T* host, size_t count) {
+        int rc = get(out, count);
+        if (rc != CCB_OK) return rc;
+        if (count) CCB_CUDA(cudaMemcpy(*out, host, count * sizeof(T), cudaMemcpyHostToDevice));
+        return CCB_OK;
+    }
+};
+#define CCB_TRY(x) do { int _rc = (x); if (_rc != CCB_OK) return _rc; } while (0)
+
+int check_device(int device, const char* who) {
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || device < 0 || device >= nd) {
+        cudaGetLastError();
+        set_error(std::string(who) + ": no such CUDA device (this library has no CPU fallback)");
+        return CCB_E_CUDA;
+    }
+    CCB_CUDA(cudaSetDevice(device));
+    return CCB_OK;
+}
+
+int check_eqcs(const HostMech& H, const int32_t* eqc, int nu, const char* who) {
+    for (int i = 0; i < nu; i++)
+        if (eqc[i] < 0 || eqc[i] >= H.ne || H.act_kind[eqc[i]] == 0) { set_error(std::string(who) + ": Only 1 DOF joints are supported"); return CCB_E_INVALID; }
+    return CCB_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
-int ccb_linearize(ccb_mech*, int32_t, int32_t, const double*, const double*, const int32_t*, int32_t, const ccb_sim_opts*, double*, double*, double*,
-                  double*, double*) {
-    set_error("ccb_linearize: not implemented yet");
-    return CCB_E_UNSUPPORTED;
+int ccb_linearize(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
+                  const ccb_sim_opts* opts, double* A, double* Bu, double* Bl, double* G, double* lambda_d) {
+    if (!m || S < 1 || !zd || nu < 0 || (nu > 0 && (!Fd || !eqc))) { set_error("ccb_linearize: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_linearize"));
+    CCB_TRY(check_device(device, "ccb_linearize"));
+    const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
+    Scratch sc;
+    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s;
+    int *d_eqc, *d_status;
+    CCB_TRY(sc.put(&d_zd, zd, (size_t)S * nb * 13));
+    CCB_TRY(sc.put(&d_Fd, Fd, (size_t)S * nu));
+    CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
+    CCB_TRY(sc.get(&d_A, (size_t)S * n * n)); CCB_TRY(sc.get(&d_Bu, (size_t)S * n * nu)); CCB_TRY(sc.get(&d_Bl, (size_t)S * n * ml));
+    CCB_TRY(sc.get(&d_G, (size_t)S * ml * n)); CCB_TRY(sc.get(&d_lam, (size_t)S * ml)); CCB_TRY(sc.get(&d_s, (size_t)S * nb * 6));
+    CCB_TRY(sc.get(&d_status, (size_t)S));
+    CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)S * ml, 1) * sizeof(double)));
+    CCB_TRY(linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+    CCB_CUDA(cudaDeviceSynchronize());
+    if (A) CCB_CUDA(cudaMemcpy(A, d_A, (size_t)S * n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Bu && nu) CCB_CUDA(cudaMemcpy(Bu, d_Bu, (size_t)S * n * nu * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Bl && ml) CCB_CUDA(cudaMemcpy(Bl, d_Bl, (size_t)S * n * ml * sizeof(double), cudaMemcpyDeviceToHost));
+    if (G && ml) CCB_CUDA(cudaMemcpy(G, d_G, (size_t)S * ml * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (lambda_d && ml) CCB_CUDA(cudaMemcpy(lambda_d, d_lam, (size_t)S * ml * sizeof(double), cudaMemcpyDeviceToHost));
+    return CCB_OK;
 }
-int ccb_dlqr(int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, const double*, const double*, const double*, const double*, const double*, int64_t,
-             const double*, int64_t, double*, int32_t*, int32_t*) {
-    set_error("ccb_dlqr: not implemented yet");
-    return CCB_E_UNSUPPORTED;
+
+int ccb_dlqr(int32_t device, int32_t S, int32_t n, int32_t nu, int32_t ml, int32_t N, const double* A, const double* Bu, const double* Bl,
+             const double* G, const double* Q, int64_t Q_bs, const double* R, int64_t R_bs, double* Ku, int32_t* kexit, int32_t* iters) {
+    if (S < 1 || n < 1 || nu < 1 || ml < 0 || N < 2 || !A || !Bu || !Q || !R || !Ku) { set_error("ccb_dlqr: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_device(device, "ccb_dlqr"));
+    Scratch sc;
+    double *d_A, *d_Bu, *d_Bl, *d_G, *d_Q, *d_R, *d_At, *d_D, *d_Ku, *d_ws1, *d_ws2;
+    int *d_kexit, *d_iters;
+    CCB_TRY(sc.put(&d_A, A, (size_t)S * n * n)); CCB_TRY(sc.put(&d_Bu, Bu, (size_t)S * n * nu));
+    CCB_TRY(sc.put(&d_Bl, Bl, (size_t)S * n * ml)); CCB_TRY(sc.put(&d_G, G, (size_t)S * ml * n));
+    CCB_TRY(sc.put(&d_Q, Q, (Q_bs ? (size_t)S : 1) * n * n)); CCB_TRY(sc.put(&d_R, R, (R_bs ? (size_t)S : 1) * nu * nu));
+    CCB_TRY(sc.get(&d_At, (size_t)S * n * n)); CCB_TRY(sc.get(&d_D, (size_t)S * n * nu));
+    CCB_TRY(sc.get(&d_Ku, (size_t)S * (N - 1) * nu * n));
+    CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
+    CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
+    CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
+    CCB_TRY(riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+    CCB_TRY(riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2, 0));
+    CCB_CUDA(cudaDeviceSynchronize());
+    CCB_CUDA(cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (kexit) CCB_CUDA(cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    if (iters) CCB_CUDA(cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    return CCB_OK;
 }
-int ccb_lqr_synthesize(ccb_mech*, int32_t, int32_t, const double*, const double*, const int32_t*, int32_t, const double*, int64_t, const double*,
-                       int64_t, int32_t, const ccb_sim_opts*, double*, int32_t*, int32_t*) {
-    set_error("ccb_lqr_synthesize: not implemented yet");
-    return CCB_E_UNSUPPORTED;
+
+int ccb_lqr_synthesize(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
+                       const double* Q, int64_t Q_bs, const double* R, int64_t R_bs, int32_t N, const ccb_sim_opts* opts, double* Ku,
+                       int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || !zd || nu < 1 || !Fd || !eqc || !Q || !R || N < 2 || !Ku) { set_error("ccb_lqr_synthesize: bad arguments"); return CCB_E_INVALID; }
+    if (m->h.ml == 0) { set_error("ccb_lqr_synthesize: mechanism without joints (reference lqr.jl:30-37 dead branch) is out of scope"); return CCB_E_UNSUPPORTED; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_lqr_synthesize"));
+    CCB_TRY(check_device(device, "ccb_lqr_synthesize"));
+    const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
+    Scratch sc;
+    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_Q, *d_R, *d_At, *d_D, *d_Ku, *d_ws1, *d_ws2;
+    int *d_eqc, *d_status, *d_kexit, *d_iters;
+    CCB_TRY(sc.put(&d_zd, zd, (size_t)S * nb * 13)); CCB_TRY(sc.put(&d_Fd, Fd, (size_t)S * nu)); CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
+    CCB_TRY(sc.put(&d_Q, Q, (Q_bs ? (size_t)S : 1) * n * n)); CCB_TRY(sc.put(&d_R, R, (R_bs ? (size_t)S : 1) * nu * nu));
+    CCB_TRY(sc.get(&d_A, (size_t)S * n * n)); CCB_TRY(sc.get(&d_Bu, (size_t)S * n * nu)); CCB_TRY(sc.get(&d_Bl, (size_t)S * n * ml));
+    CCB_TRY(sc.get(&d_G, (size_t)S * ml * n)); CCB_TRY(sc.get(&d_lam, (size_t)S * ml)); CCB_TRY(sc.get(&d_s, (size_t)S * nb * 6));
+    CCB_TRY(sc.get(&d_status, (size_t)S)); CCB_TRY(sc.get(&d_At, (size_t)S * n * n)); CCB_TRY(sc.get(&d_D, (size_t)S * n * nu));
+    CCB_TRY(sc.get(&d_Ku, (size_t)S * (N - 1) * nu * n));
+    CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
+    CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
+    CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
+    CCB_CUDA(cudaMemset(d_lam, 0, (size_t)S * ml * sizeof(double)));
+    CCB_TRY(linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+    CCB_TRY(riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+    CCB_TRY(riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2, 0));
+    CCB_CUDA(cudaDeviceSynchronize());
+    CCB_CUDA(cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (kexit) CCB_CUDA(cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    if (iters) CCB_CUDA(cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    return CCB_OK;
 }
-int ccb_tracking_synthesize(ccb_mech*, int32_t, int32_t, int32_t, const double*, const double*, const int32_t*, int32_t, const double*,
-                            const double*, const ccb_sim_opts*, double*, int32_t*, int32_t*) {
-    set_error("ccb_tracking_synthesize: not implemented yet");
-    return CCB_E_UNSUPPORTED;
+
+int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
+                            int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku, int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || N < 2 || !traj || !Ftau || nu < 1 || !eqc || !Q || !R || !Ku) { set_error("ccb_tracking_synthesize: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_synthesize"));
+    CCB_TRY(check_device(device, "ccb_tracking_synthesize"));
+    const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
+    // every (trajectory, k) linearisation is independent (lqr_tracking.jl:88); only Pk carries the recursion.
+    // Chunk over trajectories so that the per-chunk matrices stay below ~6 GB.
+    const size_t per_traj = (size_t)N * ((size_t)2 * n * n + 2 * (size_t)n * nu + 2 * (size_t)n * ml) * sizeof(double);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)6 << 30) / std::max<size_t>(per_traj, 1)));
+    Scratch sc;
+    double *d_Q, *d_R;
+    int* d_eqc;
+    CCB_TRY(sc.put(&d_Q, Q, (size_t)n * n)); CCB_TRY(sc.put(&d_R, R, (size_t)nu * nu)); CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
+    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_At, *d_D, *d_Ku, *d_ws1, *d_ws2;
+    int *d_status, *d_kexit, *d_iters;
+    const size_t P = (size_t)chunk * N;
+    CCB_TRY(sc.get(&d_zd, P * nb * 13)); CCB_TRY(sc.get(&d_Fd, P * nu));
+    CCB_TRY(sc.get(&d_A, P * n * n)); CCB_TRY(sc.get(&d_Bu, P * n * nu)); CCB_TRY(sc.get(&d_Bl, P * n * ml)); CCB_TRY(sc.get(&d_G, P * ml * n));
+    CCB_TRY(sc.get(&d_lam, P * ml)); CCB_TRY(sc.get(&d_s, P * nb * 6)); CCB_TRY(sc.get(&d_status, P));
+    CCB_TRY(sc.get(&d_At, P * n * n)); CCB_TRY(sc.get(&d_D, P * n * nu));
+    CCB_TRY(sc.get(&d_Ku, (size_t)chunk * (N - 1) * nu * n));
+    CCB_TRY(sc.get(&d_ws1, P * riccati_project_ws_doubles(n, nu, ml)));
+    CCB_TRY(sc.get(&d_ws2, (size_t)chunk * riccati_sweep_ws_doubles(n, nu)));
+    CCB_TRY(sc.get(&d_kexit, (size_t)chunk)); CCB_TRY(sc.get(&d_iters, (size_t)chunk));
+    for (int s0 = 0; s0 < S; s0 += chunk) {
+        const int cs = std::min(chunk, S - s0);
+        const int Pc = cs * N;
+        CCB_CUDA(cudaMemcpy(d_zd, traj + (size_t)s0 * N * nb * 13, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
+        CCB_CUDA(cudaMemcpy(d_Fd, Ftau + (size_t)s0 * N * nu, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
+        CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)Pc * ml, 1) * sizeof(double)));
+        CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+        CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+        CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
+                                     0, d_Ku, d_kexit, d_iters, d_ws2, 0));
+        CCB_CUDA(cudaDeviceSynchronize());
+        CCB_CUDA(cudaMemcpy(Ku + (size_t)s0 * (N - 1) * nu * n, d_Ku, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (kexit) CCB_CUDA(cudaMemcpy(kexit + s0, d_kexit, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
+        if (iters) CCB_CUDA(cudaMemcpy(iters + s0, d_iters, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return CCB_OK;
 }
-}
+
+}  // extern "C"

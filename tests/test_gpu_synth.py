@@ -1,0 +1,106 @@
+"""GPU parity tests of linearsystem (K2) and the constrained Riccati recursion (K3) against the CPU oracle.
+Tolerance 1e-9 relative on A, Bu, Bλ, G and on the gains (north_star)."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import cartpole_states, oracle_lqr_gains, rel_err, zd_of
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "acrobot", "triple_cartpole", "npend8"])
+def test_linearsystem_matches_oracle(cc, orc, name):
+    mech, cfg = cc.examples.cartpole_n_pendulum(8) if name == "npend8" else getattr(cc.examples, name)()
+    om = orc.OracleMech(mech.desc())
+    eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    rng = np.random.default_rng(7)
+    S = 3
+    zd = np.repeat(zd_of(mech, cfg)[None], S, axis=0)
+    Fd = np.zeros((S, len(eqc_idx)))
+    # second setpoint: non-zero desired input and velocities (tracking-style linearisation point)
+    Fd[1] = rng.normal(size=len(eqc_idx))
+    zd[2, :, 7:13] = 0.05 * rng.normal(size=(mech.nb, 6))
+    A, Bu, Bl, G, lam = cc.linearsystem(mech, zd, Fd, eqc_idx, want_lambda=True)
+    for s in range(S):
+        ref = om.linearize(zd[s], Fd[s], eqc_idx)
+        assert rel_err(lam[s], ref["lam"]) < 1e-8
+        assert rel_err(A[s], ref["A"]) < TOL, (name, s)
+        assert rel_err(Bu[s], ref["Bu"]) < TOL
+        assert rel_err(Bl[s], ref["Bl"]) < TOL
+        assert rel_err(G[s], ref["G"]) < TOL
+
+
+def test_dlqr_matches_oracle_random_and_unconstrained(cc, orc):
+    rng = np.random.default_rng(11)
+    S, n, nu, ml, N = 5, 10, 2, 3, 60
+    A = rng.normal(size=(S, n, n)) * 0.3
+    Bu = rng.normal(size=(S, n, nu)); Bl = rng.normal(size=(S, n, ml)); G = rng.normal(size=(S, ml, n))
+    Q = np.eye(n) * 0.01; R = np.eye(nu) * 0.02
+    out = cc.dlqr(A, Bu, Bl, G, Q, R, N)
+    for s in range(S):
+        ref = orc.dlqr(A[s], Bu[s], Bl[s], G[s], Q, R, N)
+        assert out["kexit"][s] == ref["kexit"] and out["iters"][s] == ref["iters"]
+        assert rel_err(out["Ku"][s], ref["Ku"]) < TOL
+    out = cc.dlqr(A, Bu, np.zeros((S, n, 0)), np.zeros((S, 0, n)), Q, R, N)
+    for s in range(S):
+        ref = orc.dlqr(A[s], Bu[s], np.zeros((n, 0)), np.zeros((0, n)), Q, R, N)
+        assert rel_err(out["Ku"][s], ref["Ku"]) < TOL
+
+
+def test_lqr_pendulum_reference_example(cc, orc):
+    # examples/lqr_pendulum.jl end to end through the reference API: LQR(...) then simulate!(mech, 10, lqr, record=true)
+    mech, cfg = cc.examples.pendulum()
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cc.getid(mech.eqconstraints), cfg["Q"], cfg["R"], math.inf, xd=cfg["xd"], qd=cfg["qd"])
+    o = oracle_lqr_gains(cc, orc, mech, cfg)
+    assert lqr.riccati_iters[0] == 451 and bool(lqr.converged[0])      # known answer and lqr.jl:41
+    assert rel_err(lqr.K[0], o["K"]) < TOL
+    ref = np.array([0, -351.97, 0, 0, -13.65, 0, -313.93, 0, 0, 2.298, 0, 0])
+    assert np.abs(lqr.K[0, 0, 0] - ref).max() < 1e-2
+    storage = cc.simulate(mech, 10.0, lqr, record=True)
+    th = 2 * np.arctan2(storage.q[0][:, 1], storage.q[0][:, 0])
+    assert abs(th[-1] - math.pi) < 1e-7
+
+
+def test_lqr_cartpole_batched_weights(cc, orc):
+    # synthesis batch with distinct (Q-scale, R-scale) per system (SURVEY 8(d) C3 style), finite horizon
+    mech, cfg = cc.examples.cartpole()
+    rng = np.random.default_rng(2)
+    S = 6
+    qs = np.exp(rng.uniform(np.log(0.1), np.log(10), S)); rs = np.exp(rng.uniform(np.log(0.1), np.log(10), S))
+    Qd = np.stack([cc.blockdiag(cfg["Q"]) * q * mech.dt for q in qs]); Rd = np.stack([cc.blockdiag(cfg["R"]) * r * mech.dt for r in rs])
+    zd = zd_of(mech, cfg)
+    N = 400
+    out = cc.lqr_synthesize(mech, np.repeat(zd[None], S, 0), np.zeros((S, 1)), [0], Qd, Rd, N)
+    om = orc.OracleMech(mech.desc())
+    lin = om.linearize(zd, [0.0], [0])
+    for s in range(S):
+        ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd[s], Rd[s], N)
+        assert out["kexit"][s] == ref["kexit"]
+        assert rel_err(out["Ku"][s], ref["Ku"]) < TOL
+
+
+def test_tracking_lqr_triple_cartpole(cc, orc):
+    # examples/trackingLQR_triple_cartpole.jl: open-loop trajectory from U, then TrackingLQR about it (short horizon here)
+    mech, cfg = cc.examples.triple_cartpole()
+    N = 120
+    U = np.load(__file__.replace("test_gpu_synth.py", "golden/triple_cartpole_U.npy"))[:N].reshape(N, 1)
+    ol = cc.OpenLoop(mech, cfg["eqcids"], U)
+    storage0 = cc.Storage(N, mech.nb)
+    st_init = mech.state_vector().copy()
+    cc.simulate(mech, storage0, ol, record=True)
+    tl = cc.TrackingLQR(mech, storage0, U.reshape(1, N, 1), cfg["eqcids"], cfg["Q"], cfg["R"])
+    om = orc.OracleMech(mech.desc())
+    ref = om.tracking_dlqr(storage0.data[:, 0], U, [0], cc.blockdiag(cfg["Q"]) * mech.dt, cc.blockdiag(cfg["R"]) * mech.dt)
+    assert tl.kexit[0] == ref["kexit"]
+    assert rel_err(tl.K[0], ref["Ku"]) < 1e-8
+    # closed loop about the trajectory from a perturbed start, GPU vs oracle with the same gains
+    mech.set_state_vector(st_init)
+    st0 = mech.state_vector()[None].copy()
+    st0[0, 0, 1] += 0.01
+    ctrl_o = om.make_ctrl(1, kind="tracking", eqc=[0], N=N, K=tl.K[0], zd=storage0.data[:, 0], Fd=U)
+    r = om.simulate(st0, N, ctrl=ctrl_o, record=True)
+    out, final, _ = cc.simulate(mech, N * mech.dt, tl, record=True, states=st0, return_status=True)
+    assert rel_err(out.data, r["storage"]) < 1e-8
