@@ -180,3 +180,18 @@ def deltabot(dt: float = 0.01, reg: float = 1e-10):
     cfg = dict(Q=Q, R=R, horizon=math.inf, xd=[b.state.xc.copy() for b in links], qd=[b.state.qc.copy() for b in links],
                eqcids=[platl.id, platr.id], Ftaud=[6.7879484, -6.7879484])
     return mech, cfg
+
+
+def sawyer(description_path: str, dt: float = 0.01):
+    """examples/lqr_sawyer.jl:8-29: sawyer_arm.urdf, floating=false, g=0; Q = 1000 I12 x 7, R = 1 x 7, horizon 20.
+    `description_path` is the URDF itself or the parsed JSON fixture (tests/golden/sawyer_arm.json)."""
+    from . import urdf
+    if description_path.endswith(".json"):
+        mech = urdf.mechanism_from_json(description_path, floating=False, g=0.0, dt=dt)
+    else:
+        mech = urdf.mechanism_from_urdf(description_path, floating=False, g=0.0, dt=dt)
+    Q = [np.eye(12) * 1000.0 for _ in range(mech.nb)]
+    R = [np.ones((1, 1)) for _ in range(mech.ne)]
+    cfg = dict(Q=Q, R=R, horizon=20.0, xd=[b.state.xc.copy() for b in mech.bodies], qd=[b.state.qc.copy() for b in mech.bodies],
+               eqcids=[e.id for e in mech.eqconstraints])
+    return mech, cfg

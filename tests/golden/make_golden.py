@@ -8,3 +8,11 @@ line = open("/root/reference/examples/trackingLQR_triple_cartpole.jl").readline(
 vals = [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line.split("=", 1)[1])]
 assert len(vals) == 1000
 np.save(__file__.replace("make_golden.py", "triple_cartpole_U.npy"), np.array(vals))
+
+# parsed parameters of the Sawyer arm (reference examples/examples_files/sawyer_arm.urdf): masses, COMs, inertia tensors,
+# joint origins/axes -- numbers only, so that the GPU box (which has no /root/reference) can build the mechanism.
+import json, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+import ccb200 as cc
+desc = cc.urdf.parse_urdf("/root/reference/examples/examples_files/sawyer_arm.urdf")
+json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_arm.json"), "w"), indent=1)

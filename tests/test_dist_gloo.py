@@ -1,0 +1,65 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank plumbing: batch sharding and the all-gather of gain tables.
+The data path itself has no collective."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ccb200 as cc
+    lo, hi = cc.dist.shard_range(total, rank, world)
+
+    def synth(lo, hi):   # stand-in for a per-shard gain synthesis: table s is filled with the value s
+        return np.stack([np.full((3, 2, 24), float(s)) for s in range(lo, hi)]) if hi > lo else np.zeros((0, 3, 2, 24))
+
+    K = cc.dist.sharded_synthesis(synth, total)
+    ok = K.shape == (total, 3, 2, 24) and all(np.all(K[s] == s) for s in range(total))
+    q.put((rank, lo, hi, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [7, 8])
+def test_shard_and_allgather_gains_world2(total):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[3] for r in res] == [True, True]
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == total     # contiguous cover of the batch
+
+
+def test_shard_range_covers_everything():
+    sys.path.insert(0, ROOT)
+    import ccb200 as cc
+    for total in (1, 5, 4096, 1023):
+        for world in (1, 2, 4, 8):
+            cuts = [cc.dist.shard_range(total, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
