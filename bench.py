@@ -98,15 +98,9 @@ def oracle_gains(cc, orc, mech, cfg, horizon):
 
 
 def gains_for(cc, mech, cfg, horizon):
-    """gain table through the product's own GPU synthesis when it is available, else from the checker"""
-    try:
-        lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], horizon, xd=cfg["xd"])
-        return lqr, "gpu"
-    except cc.CcbError:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import orc
-        _, K, N, zd, _ = oracle_gains(cc, orc, mech, cfg, horizon)
-        return cc.LQR.from_gains(mech, cfg["eqcids"], K, N, xd=cfg["xd"]), "oracle"
+    """gain table from the product's own GPU synthesis (K2 linearsystem + K3 Riccati); fails loudly without the CUDA library"""
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], horizon, xd=cfg["xd"])
+    return lqr, "gpu"
 
 
 def cpu_reference_run(steps, warmup, sample_systems=None):

@@ -105,8 +105,8 @@ class Batch:
         check(_lib.lib().ccb_batch_sync(self.h))
 
     def simulate(self, ctrl=None, k0: int = 1, steps: int = 1, record: bool = False, eps: float = 1e-10, newton_iter: int = 100,
-                 line_iter: int = 10, lanes: int = 0, want_status: bool = True):
-        opts = _lib.SimOpts(eps, newton_iter, line_iter, lanes, 0)
+                 line_iter: int = 10, lanes: int = 0, want_status: bool = True, spw: int = 0):
+        opts = _lib.SimOpts(eps, newton_iter, line_iter, lanes, spw)
         storage = np.empty((steps, self.B, self.mh.nb, 13)) if record else None
         status = np.empty(self.B, dtype=np.int32) if want_status else None
         ch = ctrl.device_handle(self.B, self.device) if ctrl is not None else None
@@ -114,9 +114,9 @@ class Batch:
         return storage, status
 
     def simulate_device(self, ctrl=None, k0: int = 1, steps: int = 1, eps: float = 1e-10, newton_iter: int = 100, line_iter: int = 10,
-                        lanes: int = 0, storage_ptr: int = 0, status_ptr: int = 0):
+                        lanes: int = 0, storage_ptr: int = 0, status_ptr: int = 0, spw: int = 0):
         """asynchronous, device-resident variant (used by bench.py's kernel-only timing)"""
-        opts = _lib.SimOpts(eps, newton_iter, line_iter, lanes, 0)
+        opts = _lib.SimOpts(eps, newton_iter, line_iter, lanes, spw)
         ch = ctrl.device_handle(self.B, self.device) if ctrl is not None else None
         check(_lib.lib().ccb_simulate_device(self.h, ch, C.c_int32(k0), C.c_int32(steps), C.byref(opts), C.c_void_p(storage_ptr or None),
                                              C.c_void_p(status_ptr or None)))

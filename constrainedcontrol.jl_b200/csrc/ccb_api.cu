@@ -219,12 +219,11 @@ int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps,
     if (ctrl) C = ctrl->v;
     SimArgs a;
     a.state = b->state; a.lambda = b->lambda; a.storage = storage_dev; a.status = status_dev;
-    a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr;
+    a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr; a.spw = opts ? opts->reserved : 0;
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
     a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;
-    int lanes = opts && opts->lanes > 0 ? opts->lanes : b->mech->h.lanes;
-    return launch_rollout(*view, C, a, lanes, b->stream);
+    return launch_rollout(*view, C, a, opts ? opts->lanes : 0, b->mech->h.lanes, b->stream);
 }
 
 int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage, int32_t* status) {

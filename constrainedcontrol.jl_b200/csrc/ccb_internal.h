@@ -70,6 +70,11 @@ struct DevMech {
     const int* bj_side;
     const int* cb_ptr;         // [nb+1]
     const int* cb_body;
+    // serial-chain fast path (ccb_rollout_chain.cu): parent / child joint and depth of every joint
+    int is_chain, chain_max_depth, chain_max_dim;
+    const int* chain_parent;
+    const int* chain_child;
+    const int* chain_depth;
     // actuation (1-DoF eqcs)
     const int* eqc_act_joint;  // [ne] or -1
     const int* eqc_act_kind;   // [ne] 0 none, 1 force, 2 torque
@@ -92,6 +97,9 @@ struct HostMech {
     std::vector<int> elim, j_soff, j_ncol, j_self, nbr_ptr, nbr_joint, nbr_cpos, nbr_pairs, acol_ptr, acol, acol_row, lat_ptr, lat_p, lat_pc0, lat_map,
         map, binc_ptr, binc_row, binc_side, bj_ptr, bj_joint, bj_side, cb_ptr, cb_body;
     int S_doubles = 0;
+    bool is_chain = false;
+    int chain_max_depth = 0, chain_max_dim = 0;
+    std::vector<int> chain_parent, chain_child, chain_depth;
     int lanes = 8;   // default lanes per system
     // per-device uploads
     struct Upload { DevMech view; void* ibuf = nullptr; void* dbuf = nullptr; };
@@ -125,11 +133,16 @@ struct SimArgs {
     int newton_iter, line_iter;
     int knot_input;     // 1: `state` already holds the knot (x2,q2,v1,w1) of a setpoint; one Newton solve, state untouched (linearsystem)
     double* s_out;      // [B][nb][6] solution (v2,w2) when knot_input
+    int spw;            // chain kernel: systems per warp (0 = automatic)
 };
 
-int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, cudaStream_t stream);
+// lanes: 0 = automatic (chain kernel when the mechanism is a serial chain, else the general kernel with default_lanes),
+// 1 = force the chain kernel, 8/16/32 = general kernel with that many lanes per system
+int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, int default_lanes, cudaStream_t stream);
+bool chain_tables(const HostMech& H, std::vector<int>& parent, std::vector<int>& child, std::vector<int>& depth, int& max_depth, int& max_dim);
+int launch_rollout_chain(const DevMech& M, const DevCtrl& C, const SimArgs& a, const int* d_parent, const int* d_child, const int* d_depth,
+                         int max_depth, int max_dim, cudaStream_t stream);
 int rollout_smem_bytes(const DevMech& M, int lanes);
-int default_lanes(const HostMech& h);
 
 }  // namespace ccb
 

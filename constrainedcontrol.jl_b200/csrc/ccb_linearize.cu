@@ -249,8 +249,8 @@ int linearize_device(HostMech* H, int device, int S, double* d_zd, const double*
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
     a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;
-    a.knot_input = 1; a.s_out = d_s;
-    rc = launch_rollout(*view, C, a, opts && opts->lanes > 0 ? opts->lanes : H->lanes, stream);
+    a.knot_input = 1; a.s_out = d_s; a.spw = 0;
+    rc = launch_rollout(*view, C, a, opts ? opts->lanes : 0, H->lanes, stream);
     if (rc != CCB_OK) return rc;
     CCB_CUDA(cudaMemsetAsync(d_A, 0, (size_t)S * n * n * sizeof(double), stream));
     if (nu > 0) CCB_CUDA(cudaMemsetAsync(d_Bu, 0, (size_t)S * n * nu * sizeof(double), stream));

@@ -210,6 +210,7 @@ int build_host_mech(const ccb_mech_desc* d, HostMech* M) {
         M->cb_body.insert(M->cb_body.end(), cb.begin(), cb.end());
         M->cb_ptr[b + 1] = (int)M->cb_body.size();
     }
+    M->is_chain = chain_tables(*M, M->chain_parent, M->chain_child, M->chain_depth, M->chain_max_depth, M->chain_max_dim);
     // default lanes per system: enough for one pass over the constraint rows, at most a warp
     int want = std::max(M->ml, 2 * nb);
     M->lanes = want <= 12 ? 8 : want <= 24 ? 16 : 32;   // measured: fewer lanes per system win (issue-bound)
@@ -230,7 +231,8 @@ int get_dev_mech(HostMech* M, int device, const DevMech** view) {
            o_nbc = addi(M->nbr_cpos), o_nbm = addi(M->nbr_pairs), o_elim = addi(M->elim), o_acp = addi(M->acol_ptr), o_ac = addi(M->acol), o_acr = addi(M->acol_row),
            o_lp = addi(M->lat_ptr), o_lpp = addi(M->lat_p), o_lpc = addi(M->lat_pc0), o_lm = addi(M->lat_map), o_map = addi(M->map),
            o_aj = addi(M->act_joint), o_ak = addi(M->act_kind), o_bjp = addi(M->bj_ptr), o_bjj = addi(M->bj_joint), o_bjs = addi(M->bj_side),
-           o_cbp = addi(M->cb_ptr), o_cbb = addi(M->cb_body);
+           o_cbp = addi(M->cb_ptr), o_cbb = addi(M->cb_body), o_chp = addi(M->chain_parent), o_chc = addi(M->chain_child),
+           o_chd = addi(M->chain_depth);
     size_t o_mass = addd(M->mass), o_in = addd(M->inertia), o_rp = addd(M->row_proj), o_p1 = addd(M->j_p1), o_p2 = addd(M->j_p2),
            o_qo = addd(M->j_qoff), o_ax = addd(M->j_axis);
     HostMech::Upload up;
@@ -249,6 +251,8 @@ int get_dev_mech(HostMech* M, int device, const DevMech** view) {
     v.acol = I + o_ac; v.acol_row = I + o_acr; v.lat_ptr = I + o_lp; v.lat_p = I + o_lpp; v.lat_pc0 = I + o_lpc; v.lat_map = I + o_lm; v.map = I + o_map;
     v.eqc_act_joint = I + o_aj; v.eqc_act_kind = I + o_ak;
     v.bj_ptr = I + o_bjp; v.bj_joint = I + o_bjj; v.bj_side = I + o_bjs; v.cb_ptr = I + o_cbp; v.cb_body = I + o_cbb;
+    v.is_chain = M->is_chain ? 1 : 0; v.chain_max_depth = M->chain_max_depth; v.chain_max_dim = M->chain_max_dim;
+    v.chain_parent = I + o_chp; v.chain_child = I + o_chc; v.chain_depth = I + o_chd;
     // shared-memory layout of one system
     int o = 0;
     const int nb = M->nb, ml = M->ml;

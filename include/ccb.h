@@ -151,8 +151,8 @@ typedef struct ccb_sim_opts {
     double eps;           /* newton! ε, default 1e-10 */
     int32_t newton_iter;  /* default 100 */
     int32_t line_iter;    /* default 10 */
-    int32_t lanes;        /* lanes per system: 0 = automatic, else 4/8/16/32 */
-    int32_t reserved;
+    int32_t lanes;        /* 0 = automatic (serial chains: one lane per joint+body), 1 = force the chain kernel, 8/16/32 = general kernel */
+    int32_t reserved;     /* chain kernel: systems per warp, 0 = automatic (tuning knob) */
 } ccb_sim_opts;
 
 int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl /* may be NULL */, int32_t k0, int32_t steps, const ccb_sim_opts* opts /* may be NULL */,

@@ -9,14 +9,14 @@ mech, cfg = cc.examples.cartpole()
 o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=20.0)
 st0 = cartpole_states(cc, mech, B)
 lqr = cc.LQR.from_gains(mech, cfg["eqcids"], o["K"], o["N"], xd=cfg["xd"])
-for lanes in (8, 16, 32):
+for lanes, spw in ((0, 0), (0, 16), (0, 8), (0, 6), (0, 4), (0, 3), (0, 2), (0, 1), (8, 0)):
     batch = cc.Batch(mech, B)
     for rep in range(3):
         batch.set_state(st0)
         t0 = time.time()
-        _, status = batch.simulate(lqr, 1, steps, lanes=lanes)
+        _, status = batch.simulate(lqr, 1, steps, lanes=lanes, spw=spw)
         dt = time.time() - t0
-    print(f"lanes={lanes} B={B} steps={steps}: {dt*1e3:.1f} ms  {B*steps/dt/1e6:.1f} M steps/s  newton/step={status.mean()/steps:.2f}", flush=True)
+    print(f"lanes={lanes} spw={spw} B={B} steps={steps}: {dt*1e3:.1f} ms  {B*steps/dt/1e6:.1f} M steps/s  newton/step={status.mean()/steps:.2f}", flush=True)
 t0 = time.time()
 ref = o["om"].simulate(st0[:64], 200, ctrl=o["om"].make_ctrl(64, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"]), nthreads=8)
 dt = time.time() - t0
