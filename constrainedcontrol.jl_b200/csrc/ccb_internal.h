@@ -72,6 +72,7 @@ struct DevMech {
     const int* cb_body;
     // serial-chain fast path (ccb_rollout_chain.cu): parent / child joint and depth of every joint
     int is_chain, chain_max_depth, chain_max_dim;
+    int rows_ok, rows_order[6];   // row-per-lane fast path (ccb_rollout_rows.cu): joint at every chain position
     const int* chain_parent;
     const int* chain_child;
     const int* chain_depth;
@@ -136,13 +137,14 @@ struct SimArgs {
     int spw;            // chain kernel: systems per warp (0 = automatic)
 };
 
-// lanes: 0 = automatic (chain kernel when the mechanism is a serial chain, else the general kernel with default_lanes),
-// 1 = force the chain kernel, 8/16/32 = general kernel with that many lanes per system
+// lanes: 0 = automatic (row-per-lane kernel K1r for short serial chains, else the chain kernel K1c for serial chains, else the
+// general kernel K1 with default_lanes), 5 = force K1r, 1 = force K1c, 8/16/32 = K1 with that many lanes per system
 int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, int default_lanes, cudaStream_t stream);
 bool chain_tables(const HostMech& H, std::vector<int>& parent, std::vector<int>& child, std::vector<int>& depth, int& max_depth, int& max_dim);
 int launch_rollout_chain(const DevMech& M, const DevCtrl& C, const SimArgs& a, const int* d_parent, const int* d_child, const int* d_depth,
                          int max_depth, int max_dim, cudaStream_t stream);
 int rollout_smem_bytes(const DevMech& M, int lanes);
+int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
 
 }  // namespace ccb
 

@@ -253,6 +253,9 @@ int get_dev_mech(HostMech* M, int device, const DevMech** view) {
     v.bj_ptr = I + o_bjp; v.bj_joint = I + o_bjj; v.bj_side = I + o_bjs; v.cb_ptr = I + o_cbp; v.cb_body = I + o_cbb;
     v.is_chain = M->is_chain ? 1 : 0; v.chain_max_depth = M->chain_max_depth; v.chain_max_dim = M->chain_max_dim;
     v.chain_parent = I + o_chp; v.chain_child = I + o_chc; v.chain_depth = I + o_chd;
+    v.rows_ok = (M->is_chain && M->nj >= 1 && M->nj <= 6 && M->chain_max_dim <= 5 && M->chain_max_depth == M->nj - 1) ? 1 : 0;
+    for (int j = 0; j < 6; j++) v.rows_order[j] = 0;
+    if (v.rows_ok) for (int j = 0; j < M->nj; j++) v.rows_order[M->chain_depth[j]] = j;
     // shared-memory layout of one system
     int o = 0;
     const int nb = M->nb, ml = M->ml;

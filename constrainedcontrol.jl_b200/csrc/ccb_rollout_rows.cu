@@ -1,0 +1,571 @@
+// csrc/ccb_rollout_rows.cu -- K1r: fused closed-loop rollout for short serial chains (pendulum, cartpole, acrobot,
+// double pendulum, triple cartpole: up to 6 joints of dimension <= 5), the headline kernel of bench.py.
+//
+// Mapping: ONE LANE owns ONE SCALAR CONSTRAINT ROW (one lambda component).  A joint is a group of 5 consecutive lanes, a
+// system of NJ joints is 5*NJ consecutive lanes in chain order (root first) and a warp holds floor(32 / (5 NJ)) systems.
+//   * the 5 lanes of a group keep the joint's child body (pose, velocities, wrench, 3x3 blocks) redundantly in registers,
+//     so body quantities need no exchange inside the group;
+//   * a lane evaluates its own constraint row, its row of Gv D^-1 and its row of the constraint Schur complement
+//     S = Gv D^-1 G^T, which is block tridiagonal for a chain: [parent block | own block | child block | rhs] = 16 registers;
+//   * S is factorised with ONE ROW PER LANE: banded elimination from the leaf row to the root row (ldu_factorization!
+//     role, no fill outside the band), then substitution root -> leaf (ldu_backsubstitution! role); a pivot costs one
+//     broadcast of the pivot row (warp shuffles) and one FMA per entry in the lanes of the two blocks it touches;
+//   * the only shared memory is the table of Jacobian rows at the knot (fixed during a step, read with broadcast loads when
+//     the rows of S are formed) and the joint constants.
+// Compared with K1c (one lane per joint, ccb_rollout_chain.cu) the dependent instruction chain of a step is ~5x shorter,
+// which is what bounds a 4096-system batch on 148 SMs; compared with K1 (ccb_rollout.cu) nothing is interpreted from
+// index tables.
+//
+// Same algorithm and semantics as K1 / K1c: simulate! loop of ConstrainedDynamics.jl with the
+// control laws of reference src/control/lqr.jl:89-139, lqr_tracking.jl:46-71, pid.jl:43-88 fused.
+#include <algorithm>
+#include "ccb_dev_math.cuh"
+#include "ccb_internal.h"
+
+namespace ccb {
+
+namespace {
+
+constexpr int kGS = 62;   // doubles per joint group in the knot-row table: 5 rows x 12 (+2: groups land in distinct banks)
+constexpr int kCS = 24;   // doubles of constants per joint: p1 3, p2 3, qoff 4, axis 3, J 9, mass 1 (+1)
+
+struct RowsOrder { int joint[6]; };
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template <int NJ>
+__global__ void __launch_bounds__(32) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int G = 5 * NJ, SPW = 32 / G;
+    double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
+    double* cst = smem + SPW * NJ * kGS;    // [NJ][kCS]
+    const int wl = threadIdx.x;
+    const int sw = wl / G;
+    const int q = wl - sw * G;
+    const int pos = q / 5, r = q - 5 * pos;         // joint position in the chain (0 = root), row in the joint
+    const bool lane_ok = sw < SPW;
+    const int sys = blockIdx.x * SPW + sw;
+    const bool valid = lane_ok && sys < A.B;
+    const int base = lane_ok ? sw * G : 0;           // first lane of my system (idle lanes shadow system slot 0, read only)
+    const int g0 = base + 5 * pos;                   // first lane of my joint group
+    const bool has_p = pos > 0, has_c = pos < NJ - 1;
+    const int gp = has_p ? g0 - 5 : g0, gc = has_c ? g0 + 5 : g0;   // parent / child group (self when absent)
+    const int plane = has_p ? g0 - 5 + r : (lane_ok ? wl : g0 + r); // lane of the parent group holding the parent body
+    const int jt = ord.joint[pos];
+    const int cjt = has_c ? ord.joint[pos + 1] : -1;
+    const int b = __ldg(M.j_child + jt);
+    const int dim = __ldg(M.j_dim + jt), r0 = __ldg(M.j_row0 + jt);
+    const bool rowpad = !valid || r >= dim;          // padding row: identity in S, zero everywhere else
+    const int rr = r < dim ? r : 0;
+    const int kind = __ldg(M.row_kind + r0 + rr);
+    const V3 pr = ldg3(M.row_proj + 3 * (r0 + rr));
+    const int act_kind = __ldg(M.eqc_act_kind + jt);       // chain mechanisms: eqc index == joint index (chain_tables)
+    const int cact_kind = has_c ? __ldg(M.eqc_act_kind + cjt) : 0;
+    const double dt = M.dt, idt = 1.0 / M.dt, c4 = 4.0 / (M.dt * M.dt);
+    const int nst = 13 * M.nb;
+    const int swz = lane_ok ? sw : 0;
+    double* gk_own = gk + (swz * NJ + pos) * kGS;
+    const double* gk_par = gk + (swz * NJ + (has_p ? pos - 1 : pos)) * kGS;
+    const double* gk_chi = gk + (swz * NJ + (has_c ? pos + 1 : pos)) * kGS;
+    const double* cj = cst + pos * kCS;
+    const double* ccj = cst + (has_c ? pos + 1 : pos) * kCS;
+
+    // ---- joint constants -> shared memory (one copy per joint position, shared by the systems of the warp)
+    for (int i = wl; i < NJ * kCS; i += 32) {
+        const int p = i / kCS, k = i - p * kCS, j = ord.joint[p], bb = __ldg(M.j_child + j);
+        double v = 0.0;
+        if (k < 3) v = __ldg(M.j_p1 + 3 * j + k);
+        else if (k < 6) v = __ldg(M.j_p2 + 3 * j + k - 3);
+        else if (k < 10) v = __ldg(M.j_qoff + 4 * j + k - 6);
+        else if (k < 13) v = __ldg(M.j_axis + 3 * j + k - 10);
+        else if (k < 22) v = __ldg(M.inertia + 9 * bb + k - 13);
+        else if (k == 22) v = __ldg(M.mass + bb);
+        cst[i] = v;
+    }
+    __syncwarp();
+    const double mass = cj[22], kdt = dt / mass;
+    const double pkdt = has_p ? dt / cst[(pos - 1) * kCS + 22] : 0.0;
+
+    // ---- state in registers: the group's body (redundant in its 5 lanes) and my multiplier
+    double z[13], s[6], lam;
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 13; i++) z[i] = A.state[(size_t)sys * nst + 13 * b + i];
+        lam = r < dim ? A.lambda[(size_t)sys * M.ml + r0 + r] : 0.0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 13; i++) z[i] = i == 3 ? 1.0 : 0.0;
+        lam = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) s[i] = 0.0;
+
+    // sum over the lanes of my system, evaluated in one fixed order so that every lane holds the same bits
+    auto sys_sum = [&](double v) {
+        const double v0 = shfl_d(v, g0), v1 = shfl_d(v, g0 + 1), v2 = shfl_d(v, g0 + 2), v3_ = shfl_d(v, g0 + 3), v4 = shfl_d(v, g0 + 4);
+        const double gs = ((v0 + v1) + (v2 + v3_)) + v4;
+        double acc = 0.0;
+#pragma unroll
+        for (int p = 0; p < NJ; p++) acc += shfl_d(gs, base + 5 * p);
+        return acc;
+    };
+
+    int total_iters = 0;
+    bool failed = false;
+
+    for (int step = 0; step < A.steps; step++) {
+        const int k = A.k0 + step;
+        if (valid && A.storage) {   // saveToStorage!: (xc,qc,vc,wc) at the start of step k; the 5 lanes interleave the 13 words
+            double* out = A.storage + ((size_t)step * A.B + sys) * nst + 13 * b;
+#pragma unroll
+            for (int i = 0; i < 13; i++)
+                if (i % 5 == r) out[i] = z[i];
+        }
+        // ---------------- control!(k) part 1: laws that read the continuous state (PID), open-loop tables
+        double u = 0.0;
+        if (C.kind == CCB_CTRL_PID || C.kind == CCB_CTRL_TABLE) {
+            double pz[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) pz[i] = shfl_d(z[i], plane);
+            if (valid && r == 0) {
+                for (int i = 0; i < C.nu; i++) {
+                    if (__ldg(C.eqc + i) != jt) continue;
+                    if (C.kind == CCB_CTRL_TABLE) {
+                        if (k >= 1 && k <= C.N) u += __ldg(C.U + (size_t)sys * C.U_bs + (size_t)(k - 1) * C.nu + i);
+                        continue;
+                    }
+                    V3 xa = {0.0, 0.0, 0.0};
+                    Q4 qa = {1.0, 0.0, 0.0, 0.0};
+                    if (has_p) { xa = v3(pz[0], pz[1], pz[2]); qa = Q4{pz[3], pz[4], pz[5], pz[6]}; }
+                    const V3 xb = v3(z[0], z[1], z[2]);
+                    const Q4 qb = {z[3], z[4], z[5], z[6]};
+                    const V3 axis = ld3(cj + 10);
+                    double coord;
+                    if (act_kind == 1) {
+                        coord = dot(axis, qrotT(qa, xb + qrot(qb, ld3(cj + 3)) - xa) - ld3(cj));
+                    } else {
+                        Q4 qe = qmul(qmul(qconj(qa), qb), qconj(ld4(cj + 6)));
+                        double nv = sqrt(qe.x * qe.x + qe.y * qe.y + qe.z * qe.z);
+                        coord = (nv == 0.0) ? 0.0 : 2.0 * atan2(nv, qe.s) * (axis.x * qe.x + axis.y * qe.y + axis.z * qe.z) / nv;
+                    }
+                    double err = __ldg(C.goal + (size_t)sys * C.goal_bs + i) - coord;
+                    if (act_kind == 2) {           // pid.jl:46-53 (Translational3 + Rotational2)
+                        const double pi = 3.14159265358979323846;
+                        if (err > pi) err -= 2.0 * pi;
+                        else if (err < -pi) err += 2.0 * pi;
+                    }
+                    double* integ = C.pid_int + (size_t)sys * C.nu + i;
+                    double* last = C.pid_last + (size_t)sys * C.nu + i;
+                    if (k == 1) *last = err;                  // pid.jl:73
+                    const double in = *integ + err * dt;      // pid.jl:76
+                    *integ = in;
+                    const double der = (err - *last) / dt;    // pid.jl:77
+                    u += __ldg(C.P + i) * err + __ldg(C.I + i) * in + __ldg(C.D + i) * der;
+                    *last = err;
+                }
+            }
+        }
+        // ---------------- knot: x2 = xc + vc dt, q2 = qc (x) w-bar(wc); Newton starts from (v1, w1)
+        if (!A.knot_input) {
+            const V3 v = v3(z[7], z[8], z[9]), w = v3(z[10], z[11], z[12]);
+            z[0] = fma(dt, v.x, z[0]); z[1] = fma(dt, v.y, z[1]); z[2] = fma(dt, v.z, z[2]);
+            const double sq = sqrt(c4 - dot(w, w));
+            const Q4 q2 = qmul(Q4{z[3], z[4], z[5], z[6]}, Q4{0.5 * dt * sq, 0.5 * dt * w.x, 0.5 * dt * w.y, 0.5 * dt * w.z});
+            z[3] = q2.s; z[4] = q2.x; z[5] = q2.y; z[6] = q2.z;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) s[i] = z[7 + i];
+        // parent's knot pose (fixed for the step)
+        V3 xa2 = {0.0, 0.0, 0.0};
+        Q4 qa2 = {1.0, 0.0, 0.0, 0.0};
+        {
+            double t[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) t[i] = shfl_d(z[i], plane);
+            if (has_p) { xa2 = v3(t[0], t[1], t[2]); qa2 = Q4{t[3], t[4], t[5], t[6]}; }
+        }
+        // ---------------- control!(k) part 2: LQR-type laws on the knot state (lqr.jl:98-108)
+        {
+            const int n = 12 * M.nb;
+            bool lqr = false;
+            const double *K = nullptr, *zd = nullptr, *Fd = nullptr;
+            if (C.kind == CCB_CTRL_LQR_INF) {
+                lqr = true;
+                K = C.K + (size_t)sys * C.K_bs; zd = C.zd + (size_t)sys * C.zd_bs; Fd = C.Fd + (size_t)sys * C.Fd_bs;
+            } else if (C.kind == CCB_CTRL_LQR_FIN) {
+                lqr = k < C.N;
+                K = C.K + (size_t)sys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)sys * C.zd_bs; Fd = C.Fd + (size_t)sys * C.Fd_bs;
+            } else if (C.kind == CCB_CTRL_TRACKING) {
+                lqr = k < C.N;
+                K = C.K + (size_t)sys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)sys * C.zd_bs + (size_t)(k - 1) * 13 * M.nb;
+                Fd = C.Fd + (size_t)sys * C.Fd_bs + (size_t)(k - 1) * C.nu;
+            }
+            if (lqr) {
+                // lane r < 4 owns one 3-vector of the body's Δz = [x2 - xd; v1 - vd; imag(qd \ q2); w1 - wd]
+                V3 dz = {0.0, 0.0, 0.0};
+                if (valid && r < 4) {
+                    const double* d = zd + 13 * b;
+                    if (r == 0) dz = v3(z[0] - __ldg(d), z[1] - __ldg(d + 1), z[2] - __ldg(d + 2));
+                    else if (r == 1) dz = v3(z[7] - __ldg(d + 7), z[8] - __ldg(d + 8), z[9] - __ldg(d + 9));
+                    else if (r == 2) dz = qvec(qmul(qconj(ldg4(d + 3)), Q4{z[3], z[4], z[5], z[6]}));
+                    else dz = v3(z[10] - __ldg(d + 10), z[11] - __ldg(d + 11), z[12] - __ldg(d + 12));
+                }
+                for (int i = 0; i < C.nu; i++) {
+                    double part = 0.0;
+                    if (valid && r < 4) {
+                        const double* Kr = K + (size_t)i * n + 12 * b + 3 * r;
+                        part = fma(__ldg(Kr), dz.x, fma(__ldg(Kr + 1), dz.y, __ldg(Kr + 2) * dz.z));
+                    }
+                    const double tot = sys_sum(part);
+                    if (valid && r == 0 && __ldg(C.eqc + i) == jt) u += __ldg(Fd + i) - tot;
+                }
+            }
+        }
+        u = shfl_d(u, g0);                       // the joint's input, known to its 5 lanes
+        double uc = shfl_d(u, gc);               // the child joint's input
+        if (!has_c) uc = 0.0;
+        // ---------------- applyFτ!: my body gets the child side of my joint's input and the parent side of my child's
+        V3 Fext = {0.0, 0.0, 0.0}, Text = {0.0, 0.0, 0.0};
+        if (C.kind != CCB_CTRL_NONE) {
+            const Q4 qb = {z[3], z[4], z[5], z[6]};
+            if (act_kind != 0 && u != 0.0) {
+                const V3 ax = u * ld3(cj + 10);
+                if (act_kind == 1) { const V3 Fb = qrot(qa2, ax); Fext = Fext + Fb; Text = Text + cross(ld3(cj + 3), qrotT(qb, Fb)); }
+                else Text = Text + qrotT(qb, qrot(qa2, ax));
+            }
+            if (has_c && uc != 0.0) {
+                const V3 ax = uc * ld3(ccj + 10);
+                if (cact_kind == 1) { Fext = Fext - qrot(qb, ax); Text = Text - cross(ld3(ccj), ax); }
+                else if (cact_kind == 2) Text = Text - ax;
+            }
+        }
+        // λ-free part of the body residual that does not change during the Newton iteration
+        double c0[6];
+        {
+            const V3 v1 = v3(z[7], z[8], z[9]), w1 = v3(z[10], z[11], z[12]);
+            const double sq1 = sqrt(c4 - dot(w1, w1));
+            const V3 Jw1 = mat3_mul(cj + 13, w1);
+            const V3 cR = cross(w1, Jw1) - sq1 * Jw1 - 2.0 * Text;
+            c0[0] = -mass * v1.x * idt - Fext.x; c0[1] = -mass * v1.y * idt - Fext.y; c0[2] = -mass * (v1.z * idt + M.g) - Fext.z;
+            c0[3] = cR.x; c0[4] = cR.y; c0[5] = cR.z;
+        }
+        // ---------------- my Jacobian row at the knot (it carries the constraint force; fixed for the step)
+        {
+            double g;
+            V3 Gax, Gap, Gbx, Gbp;
+            row_eval(kind, pr, ld3(cj), ld3(cj + 3), ld4(cj + 6), xa2, qa2, v3(z[0], z[1], z[2]), Q4{z[3], z[4], z[5], z[6]}, true, g, Gax, Gap, Gbx, Gbp);
+            if (!has_p) { Gax = v3(0.0, 0.0, 0.0); Gap = Gax; }
+            if (rowpad) { Gax = v3(0.0, 0.0, 0.0); Gap = Gax; Gbx = Gax; Gbp = Gax; }
+            __syncwarp();
+            if (lane_ok) {
+                double* o = gk_own + 12 * r;
+                st3(o, Gax); st3(o + 3, Gap); st3(o + 6, Gbx); st3(o + 9, Gbp);
+            }
+            __syncwarp();
+        }
+        // transposed copies for the force sums: lane r owns component r of G_own,B^T λ_own + G_child,A^T λ_child
+        double FB[5], FA[5], FB5[5], FA5[5];
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            FB[t] = gk_own[12 * t + 6 + r];
+            FB5[t] = gk_own[12 * t + 11];
+            FA[t] = has_c ? gk_chi[12 * t + r] : 0.0;
+            FA5[t] = has_c ? gk_chi[12 * t + 5] : 0.0;
+        }
+
+        // ---------------- newton! with lineSearch!
+        double p3[7], Dinv[9], Mw[9], d[6];
+        double rowP[5], rowO[5], rowC[5], rhs;     // my row of S: parent block | own block | child block | rhs
+        // G^T-type sum over the rows acting on my body: own joint (child side) + child joint (parent side)
+        auto force_sum = [&](double mine, double* out6) {
+            double f = 0.0, f5 = 0.0;
+#pragma unroll
+            for (int t = 0; t < 5; t++) {
+                const double lo = shfl_d(mine, g0 + t), lc = shfl_d(mine, gc + t);
+                f = fma(FB[t], lo, fma(FA[t], lc, f));
+                f5 = fma(FB5[t], lo, fma(FA5[t], lc, f5));
+            }
+#pragma unroll
+            for (int c = 0; c < 5; c++) out6[c] = shfl_d(f, g0 + c);
+            out6[5] = f5;
+        };
+        auto evaluate = [&](bool jac) -> double {
+            const V3 v2 = v3(s[0], s[1], s[2]), w2 = v3(s[3], s[4], s[5]);
+            const double sq2 = sqrt(c4 - dot(w2, w2));
+            {
+                p3[0] = fma(dt, v2.x, z[0]); p3[1] = fma(dt, v2.y, z[1]); p3[2] = fma(dt, v2.z, z[2]);
+                const Q4 q3 = qmul(Q4{z[3], z[4], z[5], z[6]}, Q4{0.5 * dt * sq2, 0.5 * dt * w2.x, 0.5 * dt * w2.y, 0.5 * dt * w2.z});
+                p3[3] = q3.s; p3[4] = q3.x; p3[5] = q3.y; p3[6] = q3.z;
+            }
+            double J[9];
+#pragma unroll
+            for (int i = 0; i < 9; i++) J[i] = cj[13 + i];
+            const V3 Jw2 = mat3_mul(J, w2);
+            const V3 dR = sq2 * Jw2 + cross(w2, Jw2);
+            double fs[6];
+            force_sum(lam, fs);
+            d[0] = fma(mass * idt, v2.x, c0[0]) - fs[0]; d[1] = fma(mass * idt, v2.y, c0[1]) - fs[1]; d[2] = fma(mass * idt, v2.z, c0[2]) - fs[2];
+            d[3] = dR.x + c0[3] - fs[3]; d[4] = dR.y + c0[4] - fs[4]; d[5] = dR.z + c0[5] - fs[5];
+            double ss = 0.0;
+            if (valid && r == 0) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) ss = fma(d[c], d[c], ss);
+            }
+            if (jac) {
+                double Dr[9], Tw[9];
+                const double w[3] = {w2.x, w2.y, w2.z}, jw[3] = {Jw2.x, Jw2.y, Jw2.z};
+                const double isq = 1.0 / sq2;
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int qq = 0; qq < 3; qq++) {
+                        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+                        const double wxJ = w[i1] * J[i2 * 3 + qq] - w[i2] * J[i1 * 3 + qq];
+                        const double jwx = (qq == i1) ? -jw[i2] : ((qq == i2) ? jw[i1] : 0.0);
+                        Dr[i * 3 + qq] = sq2 * J[i * 3 + qq] + wxJ - jwx - jw[i] * w[qq] * isq;
+                    }
+                inv3(Dr, Dinv);
+                const double c = 0.25 * dt * dt;
+                Tw[0] = c * (w[0] * w[0] * isq + sq2); Tw[1] = c * (w[0] * w[1] * isq + w[2]); Tw[2] = c * (w[0] * w[2] * isq - w[1]);
+                Tw[3] = c * (w[1] * w[0] * isq - w[2]); Tw[4] = c * (w[1] * w[1] * isq + sq2); Tw[5] = c * (w[1] * w[2] * isq + w[0]);
+                Tw[6] = c * (w[2] * w[0] * isq + w[1]); Tw[7] = c * (w[2] * w[1] * isq - w[0]); Tw[8] = c * (w[2] * w[2] * isq + sq2);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int qq = 0; qq < 3; qq++) Mw[i * 3 + qq] = fma(Tw[i * 3], Dinv[qq], fma(Tw[i * 3 + 1], Dinv[3 + qq], Tw[i * 3 + 2] * Dinv[6 + qq]));
+            }
+            // parent body's pose (and, for the Jacobian, its residual and Tw D^-1) from the parent group
+            V3 xa3 = {0.0, 0.0, 0.0};
+            Q4 qa3 = {1.0, 0.0, 0.0, 0.0};
+            {
+                double t[7];
+#pragma unroll
+                for (int i = 0; i < 7; i++) t[i] = shfl_d(p3[i], plane);
+                if (has_p) { xa3 = v3(t[0], t[1], t[2]); qa3 = Q4{t[3], t[4], t[5], t[6]}; }
+            }
+            double g;
+            V3 Gax, Gap, Gbx, Gbp;
+            row_eval(kind, pr, ld3(cj), ld3(cj + 3), ld4(cj + 6), xa3, qa3, v3(p3[0], p3[1], p3[2]), Q4{p3[3], p3[4], p3[5], p3[6]}, jac, g, Gax, Gap, Gbx, Gbp);
+            if (rowpad) g = 0.0;
+            ss = fma(g, g, ss);
+            rhs = g;
+            if (jac) {
+                double pd[6], pM[9];
+#pragma unroll
+                for (int i = 0; i < 6; i++) pd[i] = shfl_d(d[i], plane);
+#pragma unroll
+                for (int i = 0; i < 9; i++) pM[i] = shfl_d(Mw[i], plane);
+                // my row of Gv D^-1:  Gv = [G_x dt, G_phi Tw],  D = blkdiag(m/dt I, Drot)
+                const double cb = dt * kdt, ca = dt * pkdt;
+                double wB[6], wA[6];
+                { const V3 t = vec_mat3(Gbp, Mw); wB[0] = cb * Gbx.x; wB[1] = cb * Gbx.y; wB[2] = cb * Gbx.z; wB[3] = t.x; wB[4] = t.y; wB[5] = t.z; }
+                { const V3 t = vec_mat3(Gap, pM); wA[0] = ca * Gax.x; wA[1] = ca * Gax.y; wA[2] = ca * Gax.z; wA[3] = t.x; wA[4] = t.y; wA[5] = t.z; }
+                if (!has_p) {
+#pragma unroll
+                    for (int c = 0; c < 6; c++) wA[c] = 0.0;
+                }
+                double acc = g;
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc = fma(-wB[c], d[c], acc);
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc = fma(-wA[c], pd[c], acc);
+                rhs = acc;
+                // my row of S against the rows of my joint, of the parent joint (through my parent body) and of the child joint
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    const double2* go = reinterpret_cast<const double2*>(gk_own + 12 * t);
+                    double so = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double2 a2 = go[c], b2 = go[3 + c];
+                        so = fma(wA[2 * c], a2.x, fma(wA[2 * c + 1], a2.y, so));
+                        so = fma(wB[2 * c], b2.x, fma(wB[2 * c + 1], b2.y, so));
+                    }
+                    rowO[t] = so;
+                    if (NJ > 1) {
+                        const double2* gpp = reinterpret_cast<const double2*>(gk_par + 12 * t + 6);
+                        const double2* gcc = reinterpret_cast<const double2*>(gk_chi + 12 * t);
+                        double sp = 0.0, sc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const double2 a2 = gpp[c], b2 = gcc[c];
+                            sp = fma(wA[2 * c], a2.x, fma(wA[2 * c + 1], a2.y, sp));
+                            sc = fma(wB[2 * c], b2.x, fma(wB[2 * c + 1], b2.y, sc));
+                        }
+                        rowP[t] = has_p ? sp : 0.0;
+                        rowC[t] = has_c ? sc : 0.0;
+                    } else {
+                        rowP[t] = 0.0; rowC[t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    if (t == r) rowO[t] += M.reg;
+                    if (rowpad) { rowO[t] = (t == r) ? 1.0 : 0.0; rowP[t] = 0.0; rowC[t] = 0.0; }
+                }
+                if (rowpad) rhs = 0.0;
+            }
+            return sqrt(sys_sum(ss));
+        };
+
+        // S dλ = rhs with one row per lane.  Elimination runs from the last row of the leaf joint to the first row of the
+        // root joint, so a pivot row only has entries to its left (parent block + own block) and the rows it updates are the
+        // earlier rows of its own block and the rows of the parent block: no fill.  On exit `rhs` holds dλ.
+        double dl = 0.0, ds[6];
+        auto solve = [&]() {
+            double myinv = 1.0;
+#pragma unroll
+            for (int pp = NJ - 1; pp >= 0; pp--) {
+#pragma unroll
+                for (int rk = 4; rk >= 0; rk--) {
+                    const int src = base + 5 * pp + rk;
+                    double piv = shfl_d(rowO[rk], src);
+                    if (!lane_ok) piv = 1.0;
+                    const double inv = 1.0 / piv;
+                    if (pos == pp && r == rk) myinv = inv;
+                    if (pp == 0 && rk == 0) break;                       // nothing left of the first row
+                    const bool same = (pos == pp) && (r < rk), par = (pos == pp - 1);
+                    const double fS = same ? rowO[rk] * inv : 0.0;       // factor when I am an earlier row of the pivot's block
+                    const double fP = par ? rowC[rk] * inv : 0.0;        // factor when I am a row of the pivot's parent block
+#pragma unroll
+                    for (int c = 0; c < rk; c++) {
+                        const double pv = shfl_d(rowO[c], src);
+                        rowO[c] = fma(-fS, pv, rowO[c]);
+                        if (pp > 0) rowC[c] = fma(-fP, pv, rowC[c]);
+                    }
+                    if (pp > 0) {
+#pragma unroll
+                        for (int c = 0; c < 5; c++) {
+                            const double pv = shfl_d(rowP[c], src);
+                            rowP[c] = fma(-fS, pv, rowP[c]);
+                            rowO[c] = fma(-fP, pv, rowO[c]);
+                        }
+                    }
+                    const double pr_ = shfl_d(rhs, src);
+                    rhs = fma(-(fS + fP), pr_, rhs);
+                }
+            }
+            // substitution, root row first: x_K = rhs_K / pivot_K, then it leaves the later rows of its block and the child block
+#pragma unroll
+            for (int pp = 0; pp < NJ; pp++) {
+#pragma unroll
+                for (int rk = 0; rk < 5; rk++) {
+                    const int src = base + 5 * pp + rk;
+                    const double xk = shfl_d(rhs * myinv, src);
+                    if (pos == pp && r == rk) rhs = xk;
+                    const double coef = (pos == pp && r > rk) ? rowO[rk] : ((pos == pp + 1) ? rowP[rk] : 0.0);
+                    rhs = fma(-coef, xk, rhs);
+                }
+            }
+            dl = rhs;
+            // body step ds = D^-1 (d + G_own,B^T dλ_own + G_child,A^T dλ_child)
+            double fs[6];
+            force_sum(dl, fs);
+            const V3 dw = mat3_mul(Dinv, v3(d[3] + fs[3], d[4] + fs[4], d[5] + fs[5]));
+            ds[0] = kdt * (d[0] + fs[0]); ds[1] = kdt * (d[1] + fs[1]); ds[2] = kdt * (d[2] + fs[2]);
+            ds[3] = dw.x; ds[4] = dw.y; ds[5] = dw.z;
+        };
+
+        bool done = !valid;
+        double normf0 = 0.0;
+        int it_used = 0;
+        for (int n = 1; n <= A.newton_iter; n++) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const bool act = !done;
+            const double nf = evaluate(true);
+            if (n == 1) normf0 = nf;
+            solve();
+            double sd = dl * dl;
+            if (r == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) sd = fma(ds[i], ds[i], sd);
+            }
+            if (!valid) sd = 0.0;
+            const double full = sqrt(sys_sum(sd));
+            double s0[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) s0[i] = s[i];
+            const double lam0 = lam;
+            // a step below eps taken from a residual below eps ends the solve whatever scale the line search would pick
+            const bool tiny = act && full < A.eps && normf0 < A.eps;
+            double alpha = 1.0, normf1 = normf0;
+            bool ls_done = !act || tiny;
+            if (tiny) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
+                lam = lam0 - dl;
+            }
+            for (int ls = 0; ls <= A.line_iter; ls++) {      // lineSearch!: s = s_prev - 2^-j step, first j with |f| decreased
+                if (__all_sync(0xffffffffu, ls_done)) break;
+                const bool la = !ls_done;
+                if (la) {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) s[i] = fma(-alpha, ds[i], s0[i]);
+                    lam = fma(-alpha, dl, lam0);
+                }
+                const double nf1 = evaluate(false);
+                if (la) {
+                    normf1 = nf1;
+                    if (nf1 >= normf0 && ls < A.line_iter) alpha *= 0.5;
+                    else ls_done = true;
+                }
+            }
+            if (act) {
+                it_used = n;
+                const double nd = alpha * full;
+                if (tiny || (nd < A.eps && normf1 < A.eps)) done = true;
+                normf0 = normf1;
+            } else {   // a finished system keeps its solution while the other systems of the warp iterate
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[i] = s0[i];
+                lam = lam0;
+            }
+        }
+        if (valid) {
+            total_iters += it_used;
+            if (!done) failed = true;
+        }
+        if (!A.knot_input) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) z[7 + i] = s[i];      // updatestate!: (xc,qc,vc,wc) <- (x2,q2,v2,w2)
+        }
+    }
+    if (valid && A.knot_input) {
+        if (r == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) A.s_out[(size_t)sys * 6 * M.nb + 6 * b + i] = s[i];
+        }
+        if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
+    } else if (valid) {
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+            if (i % 5 == r) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
+        if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
+    }
+    if (valid && A.status && q == 0) A.status[sys] = failed ? -total_iters : total_iters;
+}
+
+}  // namespace
+
+// Eligibility (M.rows_ok, set in get_dev_mech): a single serial chain (every joint at a distinct depth) of at most 6 joints,
+// each of dimension <= 5.
+int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream) {
+    RowsOrder ord;
+    for (int j = 0; j < 6; j++) ord.joint[j] = M.rows_order[j];
+    const int G = 5 * M.nj, spw = 32 / G;
+    const int grid = (a.B + spw - 1) / spw;
+    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS) * sizeof(double);
+    switch (M.nj) {
+        case 1: rollout_rows_kernel<1><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        case 2: rollout_rows_kernel<2><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        case 3: rollout_rows_kernel<3><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        case 4: rollout_rows_kernel<4><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        case 5: rollout_rows_kernel<5><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        default: rollout_rows_kernel<6><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+    }
+    g_launches++;
+    CCB_CUDA(cudaGetLastError());
+    return CCB_OK;
+}
+
+}  // namespace ccb

@@ -35,7 +35,7 @@ def test_pendulum_lqr_inf_c1(cc, orc):
     assert abs(th[-1] - math.pi) < 1e-7
 
 
-@pytest.mark.parametrize("lanes", [0, 8, 32])
+@pytest.mark.parametrize("lanes", [0, 5, 1, 8, 32])   # auto (K1r), K1r, K1c, K1 with 8 / 32 lanes
 def test_cartpole_lqr_finite_batch(cc, orc, lanes):
     mech, cfg = cc.examples.cartpole()
     o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=3.0)

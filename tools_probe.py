@@ -9,7 +9,7 @@ mech, cfg = cc.examples.cartpole()
 o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=20.0)
 st0 = cartpole_states(cc, mech, B)
 lqr = cc.LQR.from_gains(mech, cfg["eqcids"], o["K"], o["N"], xd=cfg["xd"])
-for lanes, spw in ((0, 0), (0, 16), (0, 8), (0, 6), (0, 4), (0, 3), (0, 2), (0, 1), (8, 0)):
+for lanes, spw in ((5, 0), (1, 16), (8, 0)):
     batch = cc.Batch(mech, B)
     for rep in range(3):
         batch.set_state(st0)
