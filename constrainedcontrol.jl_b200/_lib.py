@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libccb.so")
+SO_PATH = os.environ.get("CCB_LIB", os.path.join(CSRC, "libccb.so"))   # CCB_LIB: kernel-variant experiments only
 _LIB = None
 
 

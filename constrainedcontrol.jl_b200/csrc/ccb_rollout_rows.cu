@@ -31,10 +31,29 @@ constexpr int kCS = 24;   // doubles of constants per joint: p1 3, p2 3, qoff 4,
 
 struct RowsOrder { int joint[6]; };
 
+// 168 registers: twelve 1-warp CTAs per SM, so the 1366 CTAs of the 4096-system cartpole batch are resident in ONE wave
+// (measured on the 4096x2000 cartpole batch: 128 -> 42.5 ms, 144 -> 40.3, 168 -> 37.9, 184 -> 48.7, 200 -> 48.1, 255 -> 43.3)
+#ifndef K1R_MAXREG
+#define K1R_MAXREG 168
+#endif
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// 1/x for the LU pivots: hardware approximation refined by two Newton steps (relative error ~1e-16, no slow path)
+__device__ __forceinline__ double rcp_fast(double x) {
+#ifdef K1R_EXACT_DIV
+    return 1.0 / x;
+#else
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#endif
+}
 
 template <int NJ>
-__global__ void __launch_bounds__(32) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
+__global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
     extern __shared__ __align__(16) double smem[];
     constexpr int G = 5 * NJ, SPW = 32 / G;
     double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
@@ -264,13 +283,11 @@ __global__ void __launch_bounds__(32) rollout_rows_kernel(const DevMech M, const
             __syncwarp();
         }
         // transposed copies for the force sums: lane r owns component r of G_own,B^T λ_own + G_child,A^T λ_child
-        double FB[5], FA[5], FB5[5], FA5[5];
+        double FB[5], FA[5];
 #pragma unroll
         for (int t = 0; t < 5; t++) {
             FB[t] = gk_own[12 * t + 6 + r];
-            FB5[t] = gk_own[12 * t + 11];
             FA[t] = has_c ? gk_chi[12 * t + r] : 0.0;
-            FA5[t] = has_c ? gk_chi[12 * t + 5] : 0.0;
         }
 
         // ---------------- newton! with lineSearch!
@@ -283,7 +300,8 @@ __global__ void __launch_bounds__(32) rollout_rows_kernel(const DevMech M, const
             for (int t = 0; t < 5; t++) {
                 const double lo = shfl_d(mine, g0 + t), lc = shfl_d(mine, gc + t);
                 f = fma(FB[t], lo, fma(FA[t], lc, f));
-                f5 = fma(FB5[t], lo, fma(FA5[t], lc, f5));
+                f5 = fma(gk_own[12 * t + 11], lo, f5);                 // sixth component: every lane, table read (broadcast)
+                if (has_c) f5 = fma(gk_chi[12 * t + 5], lc, f5);
             }
 #pragma unroll
             for (int c = 0; c < 5; c++) out6[c] = shfl_d(f, g0 + c);
@@ -421,7 +439,7 @@ __global__ void __launch_bounds__(32) rollout_rows_kernel(const DevMech M, const
                     const int src = base + 5 * pp + rk;
                     double piv = shfl_d(rowO[rk], src);
                     if (!lane_ok) piv = 1.0;
-                    const double inv = 1.0 / piv;
+                    const double inv = rcp_fast(piv);
                     if (pos == pp && r == rk) myinv = inv;
                     if (pp == 0 && rk == 0) break;                       // nothing left of the first row
                     const bool same = (pos == pp) && (r < rk), par = (pos == pp - 1);

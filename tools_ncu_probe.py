@@ -5,11 +5,12 @@ import numpy as np, ccb200 as cc, orc
 from helpers import oracle_lqr_gains, cartpole_states
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 mech, cfg = cc.examples.cartpole()
 o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=20.0)
-st0 = cartpole_states(cc, mech, 4096)
+st0 = np.tile(cartpole_states(cc, mech, 4096), (B // 4096 + 1, 1, 1))[:B].copy()
 lqr = cc.LQR.from_gains(mech, cfg["eqcids"], o["K"], o["N"], xd=cfg["xd"])
-batch = cc.Batch(mech, 4096)
+batch = cc.Batch(mech, B)
 batch.set_state(st0)
 _, status = batch.simulate(lqr, 1, steps, lanes=lanes)
 print("ok", status.mean() / steps)
