@@ -10,6 +10,7 @@
 // so the device does  (1) `project`: Ã, D once per linearisation (LU with partial pivoting of G Bλ), and
 // (2) `sweep`: k = N-1 .. 1 with the early break ‖P - P+‖_F < 1e-5 (lqr.jl:172) and the back-fill (lqr.jl:179-181).
 // One CTA per system; matrices live in a global workspace (L1/L2 resident for the small mechanisms).
+#include <cstdlib>
 #include "ccb_dev_math.cuh"
 #include "ccb_internal.h"
 
@@ -241,6 +242,11 @@ __global__ void __launch_bounds__(RT) riccati_sweep_kernel(int n, int nu, int N,
 
 }  // namespace
 
+bool riccati_dmma_eligible(int n, int nu);
+int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
+                              long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
+                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream);
+
 size_t riccati_project_ws_doubles(int n, int nu, int ml) { return (size_t)ml * ml + (size_t)ml * (n + nu); }
 size_t riccati_sweep_ws_doubles(int n, int nu) { return 4 * (size_t)n * n + 2 * (size_t)nu * n; }
 
@@ -256,6 +262,9 @@ int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const do
                          long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                          int* kexit, int* iters, double* ws, cudaStream_t stream) {
     if (nu > 8) { set_error("riccati: more than 8 controlled eqcs is not supported yet"); return CCB_E_UNSUPPORTED; }
+    if (riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA"))      // K4: FP64 tensor-core sweep, P / Abar resident in shared memory
+        return riccati_sweep_dmma_device(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws,
+                                         (long long)riccati_sweep_ws_doubles(n, nu), stream);
     riccati_sweep_kernel<<<S, RT, 0, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws);
     g_launches++;
     CCB_CUDA(cudaGetLastError());

@@ -1,0 +1,296 @@
+// csrc/ccb_riccati_dmma.cu -- K4: the constrained Riccati sweep with FP64 tensor-core tiles (mma.sync.m8n8k4.f64 = SASS DMMA).
+//
+// Same recursion as K3 (ccb_riccati.cu; reference src/control/lqr.jl:141-184 and src/control/lqr_tracking.jl:87-115) on the
+// constraint-projected pair (Ã, D):
+//     Ku = (R + D'P D)^-1 D'P Ã ,   Abar = Ã - D Ku ,   P+ = Q + Ku'R Ku + Abar'P Abar ,   break if ‖P - P+‖_F < 1e-5
+// One CTA per system, T = ceil(n/8) warps, warp w owns the 8-row strip w of every n x n product.  P (later W = P Abar) and
+// Abar stay in shared memory for the whole sweep (2 n^2 doubles: 113 KB for the Sawyer arm, 187 KB for the 8-pendulum), the
+// skinny nu-row operands (D'P, Ku, R Ku, D) next to them; Ã, D, Q are read from global memory (L2) in fragment layout and a
+// copy of P lives in global memory for the ‖P - P+‖ test.  nu is padded to 8 (one tile row).  Leading dimensions are chosen
+// so that every fragment load (8 rows x 4 doubles, or 4 rows x 8 doubles) is bank-conflict free: ld mod 16 in {4, 12}.
+//
+// Fragment layout of mma.sync.aligned.m8n8k4.row.col.f64 (g = lane >> 2, t = lane & 3):
+//     a = A[g][t]      b = B[t][g]      c0,c1 = C[g][2t], C[g][2t+1]
+#include "ccb_internal.h"
+
+namespace ccb {
+
+namespace {
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int dmma_ld(int n) { return (n % 16 == 4 || n % 16 == 12) ? n : n + 4; }
+
+template <int T>
+__global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int nu, int N, const double* __restrict__ At, const double* __restrict__ D,
+                                                                     long long stride_t_A, long long stride_t_D, long long stride_s_A,
+                                                                     long long stride_s_D, const double* __restrict__ Q, long long Q_bs,
+                                                                     const double* __restrict__ R, long long R_bs, double* __restrict__ Ku,
+                                                                     int* __restrict__ kexit, int* __restrict__ iters, double* __restrict__ ws,
+                                                                     long long ws_stride) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int NT = 32 * T;
+    const int LD = dmma_ld(n);
+    double* Ps = sm;                          // [n][LD]  P, then W = P Abar
+    double* As = Ps + (size_t)n * LD;         // [n][LD]  Abar
+    double* DtP = As + (size_t)n * LD;        // [8][LD]  D'P
+    double* Kk = DtP + 8 * LD;                // [8][LD]  rhs, then Ku (rows >= nu are zero)
+    double* RK = Kk + 8 * LD;                 // [8][LD]  R Ku
+    double* Dp = RK + 8 * LD;                 // [n][8]   D padded to 8 columns
+    double* Sc = Dp + (size_t)n * 8;          // [8][8]   R + D'P D
+    double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
+    double* red = Rs + 64;                    // [T] partial sums
+    __shared__ int brk;
+
+    const size_t s = blockIdx.x;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const size_t nn = (size_t)n * n;
+    double* Pg = ws + s * ws_stride;          // global copy of P
+    const double* Qs = Q + s * Q_bs;
+    const double* Rg = R + s * R_bs;
+    double* Kout = Ku + s * (size_t)(N - 1) * nu * n;
+    const int i0 = 8 * w;                                     // my strip
+    const int ra = min(i0 + g, n - 1);                        // clamped row of my A fragments / C fragments
+    const bool row_ok = i0 + g < n;
+    int cbj[T];                                               // clamped column of my B fragment in tile column j
+    bool ok0[T], ok1[T];                                      // which of my two C elements of tile column j exist
+#pragma unroll
+    for (int j = 0; j < T; j++) { cbj[j] = min(8 * j + g, n - 1); ok0[j] = row_ok && 8 * j + 2 * t4 < n; ok1[j] = row_ok && 8 * j + 2 * t4 + 1 < n; }
+    double* ps_c = Ps + (size_t)ra * LD + 2 * t4;             // my C elements of tile column j are at [8 j], [8 j + 1]
+    double* as_c = As + (size_t)ra * LD + 2 * t4;
+    double* pg_c = Pg + (size_t)ra * n + 2 * t4;
+    const double* q_c = Qs + (size_t)ra * n + 2 * t4;
+
+    for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
+    for (int e = tid; e < 64; e += NT) { const int i = e >> 3, j = e & 7; Rs[e] = (i < nu && j < nu) ? Rg[i * nu + j] : (i == j ? 1.0 : 0.0); }
+    for (int e = tid; e < 8 * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
+    __syncthreads();
+
+    int k, it = 0;
+    for (k = N - 1; k >= 1; k--) {                            // lqr.jl:150
+        it++;
+        const double* Ak = At + s * stride_s_A + (size_t)(k - 1) * stride_t_A;
+        const double* Dk = D + s * stride_s_D + (size_t)(k - 1) * stride_t_D;
+        if (it == 1 || stride_t_D != 0) {
+            for (int e = tid; e < n * 8; e += NT) { const int i = e >> 3, j = e & 7; Dp[e] = j < nu ? Dk[(size_t)i * nu + j] : 0.0; }
+            __syncthreads();
+        }
+        // ---- (A) D'P: tile column w.  a = D^T fragment, b = P fragment
+        {
+            const int j0 = 8 * w, cb = min(j0 + g, n - 1);
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int k0 = 0; k0 < n; k0 += 8) {
+                dmma(c0, c1, Dp[(k0 + t4) * 8 + g], Ps[(size_t)(k0 + t4) * LD + cb]);
+                if (k0 + 4 < n) dmma(e0, e1, Dp[(k0 + 4 + t4) * 8 + g], Ps[(size_t)(k0 + 4 + t4) * LD + cb]);
+            }
+            const int col = j0 + 2 * t4;
+            if (col < n) DtP[g * LD + col] = c0 + e0;
+            if (col + 1 < n) DtP[g * LD + col + 1] = c1 + e1;
+        }
+        __syncthreads();
+        // ---- (B) rhs = D'P Ã (tile column w; Ã from global) and Sc = R + D'P D (warp 0)
+        {
+            const int j0 = 8 * w, cb = min(j0 + g, n - 1);
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            const double* ag = Ak + (size_t)t4 * n + cb;
+            const double* dr = DtP + g * LD + t4;
+            int k0 = 0;
+            for (; k0 + 16 <= n; k0 += 16) {                              // four independent global loads in flight
+                const double b0 = __ldg(ag), b1 = __ldg(ag + 4 * (size_t)n), b2 = __ldg(ag + 8 * (size_t)n), b3 = __ldg(ag + 12 * (size_t)n);
+                dmma(c0, c1, dr[k0], b0); dmma(e0, e1, dr[k0 + 4], b1); dmma(c0, c1, dr[k0 + 8], b2); dmma(e0, e1, dr[k0 + 12], b3);
+                ag += 16 * (size_t)n;
+            }
+            for (; k0 < n; k0 += 4) { dmma(c0, c1, dr[k0], __ldg(ag)); ag += 4 * (size_t)n; }
+            const int col = j0 + 2 * t4;
+            if (col < n) Kk[g * LD + col] = c0 + e0;
+            if (col + 1 < n) Kk[g * LD + col + 1] = c1 + e1;
+            if (w == 0) {
+                double s0 = Rs[g * 8 + 2 * t4], s1 = Rs[g * 8 + 2 * t4 + 1];
+                for (int k0 = 0; k0 < n; k0 += 4) dmma(s0, s1, DtP[g * LD + k0 + t4], Dp[(k0 + t4) * 8 + g]);
+                Sc[g * 8 + 2 * t4] = s0; Sc[g * 8 + 2 * t4 + 1] = s1;
+            }
+        }
+        __syncthreads();
+        // ---- (C) Ku = Sc^-1 rhs
+        if (nu == 1) {                                                   // scalar input: Ku = rhs / Sc
+            const double inv = 1.0 / Sc[0], r00 = Rs[0];
+            for (int c = tid; c < n; c += NT) {
+                const double x0 = Kk[c] * inv;
+                Kk[c] = x0;
+                Kout[(size_t)(k - 1) * n + c] = x0;                          // lqr.jl:162-164
+                RK[c] = r00 * x0;
+            }
+        } else {
+            // Sc = R + D'P D is symmetric positive definite: elimination without pivoting, redundantly per thread in registers
+            for (int c = tid; c < n; c += NT) {
+                double Mx[8][8], x[8], invd[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    x[i] = Kk[i * LD + c];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) Mx[i][j] = Sc[i * 8 + j];
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) {
+                    invd[cc] = 1.0 / Mx[cc][cc];
+#pragma unroll
+                    for (int i = cc + 1; i < 8; i++) {
+                        const double l = Mx[i][cc] * invd[cc];
+#pragma unroll
+                        for (int j = cc + 1; j < 8; j++) Mx[i][j] = fma(-l, Mx[cc][j], Mx[i][j]);
+                        x[i] = fma(-l, x[cc], x[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 7; i >= 0; i--) {
+#pragma unroll
+                    for (int j = i + 1; j < 8; j++) x[i] = fma(-Mx[i][j], x[j], x[i]);
+                    x[i] *= invd[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    Kk[i * LD + c] = x[i];
+                    if (i < nu) Kout[(size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];      // lqr.jl:162-164
+                    double acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc = fma(Rs[i * 8 + j], x[j], acc);
+                    RK[i * LD + c] = i < nu ? acc : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (D) Abar = Ã - D Ku  (strip w; rank-8 update of Ã read from global in C layout)          lqr.jl:169
+        double acc[T][2];
+        {
+            const double* a_c = Ak + (size_t)ra * n + 2 * t4;
+#pragma unroll
+            for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? __ldg(a_c + 8 * j) : 0.0; acc[j][1] = ok1[j] ? __ldg(a_c + 8 * j + 1) : 0.0; }
+            const double a0 = -Dp[ra * 8 + t4], a1 = -Dp[ra * 8 + 4 + t4];
+            const double *k0row = Kk + t4 * LD, *k1row = Kk + (4 + t4) * LD;
+#pragma unroll
+            for (int j = 0; j < T; j++) {
+                dmma(acc[j][0], acc[j][1], a0, k0row[cbj[j]]);
+                dmma(acc[j][0], acc[j][1], a1, k1row[cbj[j]]);
+                if (ok0[j]) as_c[8 * j] = acc[j][0];
+                if (ok1[j]) as_c[8 * j + 1] = acc[j][1];
+            }
+        }
+        __syncthreads();
+        // ---- (E) W = P Abar (strip w), kept in registers until every warp has finished reading P
+#pragma unroll
+        for (int j = 0; j < T; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+        {
+            const double* arow = Ps + (size_t)ra * LD + t4;
+            const double* brow = As + (size_t)t4 * LD;
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const double a = arow[k0];
+#pragma unroll
+                for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+                brow += 4 * LD;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < T; j++) {                                    // old P -> global copy (for the ‖P - P+‖ test), W -> shared
+            if (ok0[j]) { pg_c[8 * j] = ps_c[8 * j]; ps_c[8 * j] = acc[j][0]; }
+            if (ok1[j]) { pg_c[8 * j + 1] = ps_c[8 * j + 1]; ps_c[8 * j + 1] = acc[j][1]; }
+        }
+        __syncthreads();
+        // ---- (F) P+ = Q + Abar' W + Ku' (R Ku)  (strip w)                                              lqr.jl:170
+#pragma unroll
+        for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? __ldg(q_c + 8 * j) : 0.0; acc[j][1] = ok1[j] ? __ldg(q_c + 8 * j + 1) : 0.0; }
+        {
+            const double* arow = As + (size_t)t4 * LD + ra;              // Abar^T fragment
+            const double* brow = Ps + (size_t)t4 * LD;                   // W
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const double a = *arow;
+#pragma unroll
+                for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+                arow += 4 * LD; brow += 4 * LD;
+            }
+        }
+#pragma unroll
+        for (int k0 = 0; k0 < 8; k0 += 4) {
+            const double a = Kk[(k0 + t4) * LD + ra];                    // Ku^T fragment
+            const double* brow = RK + (k0 + t4) * LD;
+#pragma unroll
+            for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+        }
+        double nd = 0.0;                                                 // ‖P - P+‖_F^2 over my fragments (old P from the global copy)
+        {
+            double po[T][2];
+#pragma unroll
+            for (int j = 0; j < T; j++) { po[j][0] = ok0[j] ? pg_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? pg_c[8 * j + 1] : acc[j][1]; }
+#pragma unroll
+            for (int j = 0; j < T; j++) { const double d0 = po[j][0] - acc[j][0], d1 = po[j][1] - acc[j][1]; nd = fma(d0, d0, nd); nd = fma(d1, d1, nd); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
+        if (lane == 0) red[w] = nd;
+        __syncthreads();                                                 // every warp is done reading W
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int q = 0; q < T; q++) tot += red[q];
+            brk = sqrt(tot) < 1e-5;                                      // lqr.jl:172
+        }
+#pragma unroll
+        for (int j = 0; j < T; j++) {                                    // lqr.jl:176  Pk = Pkp1
+            if (ok0[j]) ps_c[8 * j] = acc[j][0];
+            if (ok1[j]) ps_c[8 * j + 1] = acc[j][1];
+        }
+        __syncthreads();
+        if (brk) break;
+    }
+    if (k < 1) k = 1;                                                    // a completed loop leaves k == 1
+    for (int k2 = k - 1; k2 >= 1; k2--) {                                // lqr.jl:179-181 back-fill
+        for (int e = tid; e < nu * n; e += NT) Kout[(size_t)(k2 - 1) * nu * n + e] = Kout[(size_t)k2 * nu * n + e];
+        __syncthreads();
+    }
+    if (tid == 0) { kexit[s] = k; iters[s] = it; }
+}
+
+size_t dmma_smem_bytes(int n, int T) {
+    const int LD = dmma_ld(n);
+    return ((size_t)2 * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + T + 8) * sizeof(double);
+}
+
+template <int T>
+int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D, long long stride_s_A,
+                long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku, int* kexit, int* iters, double* ws,
+                long long ws_stride, cudaStream_t stream) {
+    const size_t smem = dmma_smem_bytes(n, T);
+    CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    riccati_sweep_dmma_kernel<T><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
+                                                             iters, ws, ws_stride);
+    g_launches++;
+    CCB_CUDA(cudaGetLastError());
+    return CCB_OK;
+}
+
+}  // namespace
+
+// n must be a multiple of 4 (it is 12 nb), nu <= 8, and 2 n^2 doubles must fit in shared memory (n <= 108)
+bool riccati_dmma_eligible(int n, int nu) {
+    if (n % 4 != 0 || nu > 8 || n < 8) return false;
+    const int T = (n + 7) / 8;
+    return T <= 14 && dmma_smem_bytes(n, T) <= 227 * 1024;
+}
+
+int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
+                              long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
+                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
+    const int T = (n + 7) / 8;
+#define CCB_DMMA_CASE(TT) \
+    case TT: return launch_dmma<TT>(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream);
+    switch (T) {
+        CCB_DMMA_CASE(1) CCB_DMMA_CASE(2) CCB_DMMA_CASE(3) CCB_DMMA_CASE(4) CCB_DMMA_CASE(5) CCB_DMMA_CASE(6) CCB_DMMA_CASE(7)
+        CCB_DMMA_CASE(8) CCB_DMMA_CASE(9) CCB_DMMA_CASE(10) CCB_DMMA_CASE(11) CCB_DMMA_CASE(12) CCB_DMMA_CASE(13) CCB_DMMA_CASE(14)
+    }
+#undef CCB_DMMA_CASE
+    set_error("riccati_dmma: unsupported size");
+    return CCB_E_UNSUPPORTED;
+}
+
+}  // namespace ccb

@@ -40,6 +40,22 @@ struct Scratch {
 };
 #define CCB_TRY(x) do { int _rc = (x); if (_rc != CCB_OK) return _rc; } while (0)
 
+// device times of the phases of the last synthesis call on this thread (CUDA events on the launching stream)
+thread_local double g_phase_ms[4] = {0, 0, 0, 0};   // linearize (K1 knot solve + K2), project, sweep (K3/K4), reserved
+struct PhaseTimer {
+    cudaEvent_t ev[4];
+    PhaseTimer() { for (auto& e : ev) cudaEventCreate(&e); }
+    ~PhaseTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+    void mark(int i) { cudaEventRecord(ev[i], 0); }
+    void finish(bool accumulate) {   // call after a device synchronisation
+        for (int i = 0; i < 3; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+            g_phase_ms[i] = (accumulate ? g_phase_ms[i] : 0.0) + ms;
+        }
+    }
+};
+
 int check_device(int device, const char* who) {
     int nd = 0;
     if (cudaGetDeviceCount(&nd) != cudaSuccess || device < 0 || device >= nd) {
@@ -102,12 +118,22 @@ int ccb_dlqr(int32_t device, int32_t S, int32_t n, int32_t nu, int32_t ml, int32
     CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
+    PhaseTimer pt;
+    pt.mark(0); pt.mark(1);
     CCB_TRY(riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+    pt.mark(2);
     CCB_TRY(riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2, 0));
+    pt.mark(3);
     CCB_CUDA(cudaDeviceSynchronize());
+    pt.finish(false);
     CCB_CUDA(cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
     if (kexit) CCB_CUDA(cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
     if (iters) CCB_CUDA(cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    return CCB_OK;
+}
+
+int ccb_synth_phase_ms(double out[4]) {
+    for (int i = 0; i < 4; i++) out[i] = g_phase_ms[i];
     return CCB_OK;
 }
 
@@ -132,10 +158,16 @@ int ccb_lqr_synthesize(ccb_mech* m, int32_t device, int32_t S, const double* zd,
     CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
     CCB_CUDA(cudaMemset(d_lam, 0, (size_t)S * ml * sizeof(double)));
+    PhaseTimer pt;
+    pt.mark(0);
     CCB_TRY(linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+    pt.mark(1);
     CCB_TRY(riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+    pt.mark(2);
     CCB_TRY(riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2, 0));
+    pt.mark(3);
     CCB_CUDA(cudaDeviceSynchronize());
+    pt.finish(false);
     CCB_CUDA(cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
     if (kexit) CCB_CUDA(cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
     if (iters) CCB_CUDA(cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
@@ -167,17 +199,23 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
     CCB_TRY(sc.get(&d_ws1, P * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)chunk * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)chunk)); CCB_TRY(sc.get(&d_iters, (size_t)chunk));
+    PhaseTimer pt;
     for (int s0 = 0; s0 < S; s0 += chunk) {
         const int cs = std::min(chunk, S - s0);
         const int Pc = cs * N;
         CCB_CUDA(cudaMemcpy(d_zd, traj + (size_t)s0 * N * nb * 13, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
         CCB_CUDA(cudaMemcpy(d_Fd, Ftau + (size_t)s0 * N * nu, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
         CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)Pc * ml, 1) * sizeof(double)));
+        pt.mark(0);
         CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+        pt.mark(1);
         CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+        pt.mark(2);
         CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
                                      0, d_Ku, d_kexit, d_iters, d_ws2, 0));
+        pt.mark(3);
         CCB_CUDA(cudaDeviceSynchronize());
+        pt.finish(s0 > 0);
         CCB_CUDA(cudaMemcpy(Ku + (size_t)s0 * (N - 1) * nu * n, d_Ku, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
         if (kexit) CCB_CUDA(cudaMemcpy(kexit + s0, d_kexit, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
         if (iters) CCB_CUDA(cudaMemcpy(iters + s0, d_iters, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));

@@ -87,3 +87,10 @@ def tracking_synthesize(mech, traj, Ftau, eqc_idx, Q, R, device: int = 0, **kw):
     check(_lib.lib().ccb_tracking_synthesize(mh.h, C.c_int32(device), C.c_int32(S), C.c_int32(N), ptr(traj), ptr(Ftau), ptr(eqc_idx), C.c_int32(nu),
                                              ptr(Q), ptr(R), C.byref(o), ptr(Ku), ptr(kexit), ptr(iters)))
     return dict(Ku=Ku, kexit=kexit, iters=iters)
+
+
+def phase_ms():
+    """device time (ms) of the phases of the last synthesis call: dict(linearize, project, sweep)"""
+    out = (C.c_double * 4)()
+    check(_lib.lib().ccb_synth_phase_ms(out))
+    return dict(linearize=out[0], project=out[1], sweep=out[2])

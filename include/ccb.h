@@ -198,6 +198,11 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
                             int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku, int32_t* kexit,
                             int32_t* iters);
 
+/* Device time (ms, CUDA events on the launching stream) of the phases of the last ccb_dlqr / ccb_lqr_synthesize /
+ * ccb_tracking_synthesize call on the calling thread: out[0] linearisation (K1 knot solve + K2), out[1] constraint projection,
+ * out[2] Riccati sweep (K3 / K4), out[3] reserved.  Measurement aid for bench.py (no reference counterpart). */
+int ccb_synth_phase_ms(double out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,9 @@ def run_lqr_config(tag, mech, cfg, st_fn, B, steps, horizon, parity_B=8, parity_
         qs = np.exp(rng.uniform(np.log(0.1), np.log(10), synth_S)); rs = np.exp(rng.uniform(np.log(0.1), np.log(10), synth_S))
         Qb = Qd[None] * qs[:, None, None]; Rb = Rd[None] * rs[:, None, None]
         t, o2 = timed(lambda: cc.lqr_synthesize(mech, np.repeat(zd[None], synth_S, 0), np.repeat(Fd[None], synth_S, 0), eqc_idx, Qb, Rb, N), reps=1)
-        rec.update(synth_S=synth_S, synth_batch_s=t, syntheses_per_s=synth_S / t, synth_mean_iters=float(o2["iters"].mean()))
+        ph = cc.synth.phase_ms()
+        rec.update(synth_S=synth_S, synth_batch_s=t, syntheses_per_s=synth_S / t, synth_mean_iters=float(o2["iters"].mean()), phase_ms=ph,
+                   syntheses_per_s_device=synth_S / (sum(ph.values()) * 1e-3))
     print(json.dumps(rec), flush=True)
 
 
