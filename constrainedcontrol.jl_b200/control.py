@@ -270,16 +270,51 @@ class LQR(Controller):
         else:
             Ntemp = int(math.ceil(10 / dt))
         self.N = N
-        from .synth import lqr_synthesize
-        res = lqr_synthesize(mech, zd, Fd, self.eqc_idx, Qd, Rd, Ntemp, device=device, **(opts or {}))
-        Ku = res["Ku"]                    # [S][Ntemp-1][nu][n]
-        self.kexit, self.riccati_iters = res["kexit"], res["iters"]
-        if N == math.inf:                 # lqr.jl:40-43
-            self.converged = np.array([np.array_equal(Ku[s, 0], Ku[s, 1]) for s in range(S)]) if Ntemp > 2 else np.ones(S, bool)
-            Ku = Ku[:, :1]
-        self.K = Ku
+        # synthesis + controller tables in one C-ABI call: the gain table stays on the device (ccb_lqr_create)
+        from .synth import _opts, _weights
+        mh = handle(mech)
+        Qw, qs = _weights(Qd, S, mh.n)
+        Rw, rs = _weights(Rd, S, nu)
+        self.kexit = np.empty(S, np.int32); self.riccati_iters = np.empty(S, np.int32); conv = np.empty(S, np.int32)
+        o = _opts(**(opts or {}))
+        h = C.c_void_p()
+        check(_lib.lib().ccb_lqr_create(mh.h, C.c_int32(device), C.c_int32(S), ptr(zd), ptr(Fd), ptr(self.eqc_idx), C.c_int32(nu), ptr(Qw), C.c_int64(qs),
+                                        ptr(Rw), C.c_int64(rs), C.c_int32(Ntemp), C.c_int32(1 if N == math.inf else 0), C.byref(o), C.byref(h),
+                                        ptr(self.kexit), ptr(self.riccati_iters), ptr(conv)))
+        self._native = (h, S, device)
+        self.converged = conv.astype(bool)          # lqr.jl:41 (Ku[1] == Ku[2]); only meaningful for horizon = Inf
+        self._K = None
+        self._rows = 1 if N == math.inf else Ntemp - 1
         self.zd, self.Fd = zd, Fd
         self.kind = CTRL_LQR_INF if N == math.inf else CTRL_LQR_FIN
+
+    @property
+    def K(self):
+        """gain table [S][rows][nu][12 nb]; fetched from the device on first use"""
+        if self._K is None:
+            h, S, _ = self._native
+            n, nu = 12 * self.mech.nb, len(self.eqcids)
+            K = np.empty((S, self._rows, nu, n))
+            check(_lib.lib().ccb_ctrl_get_gains(h, C.c_int32(n), ptr(K), C.c_int64(K.size)))
+            self._K = K
+        return self._K
+
+    @K.setter
+    def K(self, v):
+        self._K = v
+
+    def device_handle(self, B: int, device: int):
+        nat = getattr(self, "_native", None)
+        if nat is not None and nat[2] == device and nat[1] in (1, B):
+            return nat[0]
+        return super().device_handle(B, device)
+
+    def invalidate(self):
+        nat = getattr(self, "_native", None)
+        if nat is not None:
+            _lib.lib().ccb_ctrl_destroy(nat[0])
+            self._native = None
+        super().invalidate()
 
     @classmethod
     def from_gains(cls, mechanism: Mechanism, eqcids, K, horizon_steps, xd=None, vd=None, qd=None, wd=None, Ftaud=None):
@@ -289,6 +324,7 @@ class LQR(Controller):
         self.mech, self.eqcids = mechanism, list(eqcids)
         self.eqc_idx = i32([mechanism.eqc_index(i) for i in eqcids])
         self.N = horizon_steps
+        self._native = None
         rows = 1 if horizon_steps == math.inf else int(horizon_steps) - 1
         self.K = f64(K).reshape(-1, rows, nu, 12 * nb)
         self.zd = _zd_array(nb, xd, vd, qd, wd)

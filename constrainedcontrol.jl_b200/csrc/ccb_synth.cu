@@ -1,6 +1,7 @@
 // csrc/ccb_synth.cu -- C-ABI entry points for linearsystem / dlqr / LQR and TrackingLQR gain synthesis (K2 + K3).
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include <vector>
 #include "ccb_internal.h"
 
@@ -137,6 +138,46 @@ int ccb_synth_phase_ms(double out[4]) {
     return CCB_OK;
 }
 
+// LQR synthesis on the device: linearsystem (K1 knot solve + K2) -> projection -> Riccati sweep (K3/K4).  The gain table
+// d_Ku [S][N-1][nu][n] is allocated here and handed to the caller (cudaFree).
+static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, const double* Fd, const int32_t* eqc, int nu, const double* Q,
+                            int64_t Q_bs, const double* R, int64_t R_bs, int N, const ccb_sim_opts* opts, double** d_Ku_out, int32_t* kexit,
+                            int32_t* iters) {
+    const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
+    Scratch sc;
+    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_Q, *d_R, *d_At, *d_D, *d_ws1, *d_ws2;
+    int *d_eqc, *d_status, *d_kexit, *d_iters;
+    CCB_TRY(sc.put(&d_zd, zd, (size_t)S * nb * 13)); CCB_TRY(sc.put(&d_Fd, Fd, (size_t)S * nu)); CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
+    CCB_TRY(sc.put(&d_Q, Q, (Q_bs ? (size_t)S : 1) * n * n)); CCB_TRY(sc.put(&d_R, R, (R_bs ? (size_t)S : 1) * nu * nu));
+    CCB_TRY(sc.get(&d_A, (size_t)S * n * n)); CCB_TRY(sc.get(&d_Bu, (size_t)S * n * nu)); CCB_TRY(sc.get(&d_Bl, (size_t)S * n * ml));
+    CCB_TRY(sc.get(&d_G, (size_t)S * ml * n)); CCB_TRY(sc.get(&d_lam, (size_t)S * ml)); CCB_TRY(sc.get(&d_s, (size_t)S * nb * 6));
+    CCB_TRY(sc.get(&d_status, (size_t)S)); CCB_TRY(sc.get(&d_At, (size_t)S * n * n)); CCB_TRY(sc.get(&d_D, (size_t)S * n * nu));
+    CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
+    CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
+    CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
+    double* d_Ku = nullptr;
+    CCB_CUDA(cudaMalloc(&d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double)));
+    auto bail = [&](int rc) { cudaFree(d_Ku); return rc; };
+    if (cudaMemset(d_lam, 0, (size_t)S * ml * sizeof(double)) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMemset"));
+    PhaseTimer pt;
+    int rc;
+    pt.mark(0);
+    if ((rc = linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0)) != CCB_OK) return bail(rc);
+    pt.mark(1);
+    if ((rc = riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0)) != CCB_OK) return bail(rc);
+    pt.mark(2);
+    if ((rc = riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2,
+                                   0)) != CCB_OK) return bail(rc);
+    pt.mark(3);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaDeviceSynchronize"));
+    pt.finish(false);
+    if (kexit && cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
+    if (iters && cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
+    *d_Ku_out = d_Ku;
+    return CCB_OK;
+}
+
 int ccb_lqr_synthesize(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
                        const double* Q, int64_t Q_bs, const double* R, int64_t R_bs, int32_t N, const ccb_sim_opts* opts, double* Ku,
                        int32_t* kexit, int32_t* iters) {
@@ -144,33 +185,94 @@ int ccb_lqr_synthesize(ccb_mech* m, int32_t device, int32_t S, const double* zd,
     if (m->h.ml == 0) { set_error("ccb_lqr_synthesize: mechanism without joints (reference lqr.jl:30-37 dead branch) is out of scope"); return CCB_E_UNSUPPORTED; }
     CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_lqr_synthesize"));
     CCB_TRY(check_device(device, "ccb_lqr_synthesize"));
-    const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
-    Scratch sc;
-    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_Q, *d_R, *d_At, *d_D, *d_Ku, *d_ws1, *d_ws2;
-    int *d_eqc, *d_status, *d_kexit, *d_iters;
-    CCB_TRY(sc.put(&d_zd, zd, (size_t)S * nb * 13)); CCB_TRY(sc.put(&d_Fd, Fd, (size_t)S * nu)); CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
-    CCB_TRY(sc.put(&d_Q, Q, (Q_bs ? (size_t)S : 1) * n * n)); CCB_TRY(sc.put(&d_R, R, (R_bs ? (size_t)S : 1) * nu * nu));
-    CCB_TRY(sc.get(&d_A, (size_t)S * n * n)); CCB_TRY(sc.get(&d_Bu, (size_t)S * n * nu)); CCB_TRY(sc.get(&d_Bl, (size_t)S * n * ml));
-    CCB_TRY(sc.get(&d_G, (size_t)S * ml * n)); CCB_TRY(sc.get(&d_lam, (size_t)S * ml)); CCB_TRY(sc.get(&d_s, (size_t)S * nb * 6));
-    CCB_TRY(sc.get(&d_status, (size_t)S)); CCB_TRY(sc.get(&d_At, (size_t)S * n * n)); CCB_TRY(sc.get(&d_D, (size_t)S * n * nu));
-    CCB_TRY(sc.get(&d_Ku, (size_t)S * (N - 1) * nu * n));
-    CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
-    CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
-    CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
-    CCB_CUDA(cudaMemset(d_lam, 0, (size_t)S * ml * sizeof(double)));
-    PhaseTimer pt;
-    pt.mark(0);
-    CCB_TRY(linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
-    pt.mark(1);
-    CCB_TRY(riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
-    pt.mark(2);
-    CCB_TRY(riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2, 0));
-    pt.mark(3);
-    CCB_CUDA(cudaDeviceSynchronize());
-    pt.finish(false);
-    CCB_CUDA(cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (kexit) CCB_CUDA(cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
-    if (iters) CCB_CUDA(cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    double* d_Ku = nullptr;
+    CCB_TRY(lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters));
+    cudaError_t e = cudaMemcpy(Ku, d_Ku, (size_t)S * (N - 1) * nu * 12 * m->h.nb * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_Ku);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(Ku)");
+    return CCB_OK;
+}
+
+// rows r of a [S][rows_all][w] table equal row r+1 ?  (lqr.jl:41 `Ku[1] != Ku[2]`)
+__global__ void rows_equal_kernel(const double* K, long long sys_stride, int w, int S, int* out) {
+    const int s = blockIdx.x;
+    __shared__ int differ;
+    if (threadIdx.x == 0) differ = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < w; i += blockDim.x)
+        if (K[(size_t)s * sys_stride + i] != K[(size_t)s * sys_stride + w + i]) differ = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) out[s] = differ ? 0 : 1;
+}
+
+int ccb_lqr_create(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu, const double* Q,
+                   int64_t Q_bs, const double* R, int64_t R_bs, int32_t N, int32_t infinite, const ccb_sim_opts* opts, ccb_ctrl** out,
+                   int32_t* kexit, int32_t* iters, int32_t* converged) {
+    if (!m || S < 1 || !zd || nu < 1 || !Fd || !eqc || !Q || !R || N < 2 || !out) { set_error("ccb_lqr_create: bad arguments"); return CCB_E_INVALID; }
+    if (m->h.ml == 0) { set_error("ccb_lqr_create: mechanism without joints (reference lqr.jl:30-37 dead branch) is out of scope"); return CCB_E_UNSUPPORTED; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_lqr_create"));
+    CCB_TRY(check_device(device, "ccb_lqr_create"));
+    const int nb = m->h.nb, n = 12 * nb;
+    double* d_Ku = nullptr;
+    CCB_TRY(lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters));
+    ccb_ctrl* c = new ccb_ctrl();
+    c->device = device; c->B = S;
+    std::memset(&c->v, 0, sizeof(c->v));
+    c->v.nu = nu;
+    auto fail = [&](int rc) { cudaFree(d_Ku); ccb_ctrl_destroy(c); return rc; };
+    const size_t row = (size_t)nu * n, rows_all = (size_t)N - 1;
+    if (converged) {
+        if (N > 2) {
+            int* d_c = nullptr;
+            if (cudaMalloc(&d_c, S * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+            rows_equal_kernel<<<S, 128>>>(d_Ku, (long long)(rows_all * row), (int)row, S, d_c);
+            g_launches++;
+            cudaError_t e = cudaMemcpy(converged, d_c, S * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(d_c);
+            if (e != cudaSuccess) return fail(cuda_fail(e, "rows_equal"));
+        } else {
+            for (int s = 0; s < S; s++) converged[s] = 1;
+        }
+    }
+    if (infinite) {   // lqr.jl:42: keep only Ku[1]
+        double* d_K1 = nullptr;
+        if (cudaMalloc(&d_K1, (size_t)S * row * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+        cudaError_t e = cudaMemcpy2D(d_K1, row * sizeof(double), d_Ku, rows_all * row * sizeof(double), row * sizeof(double), S, cudaMemcpyDeviceToDevice);
+        cudaFree(d_Ku);
+        d_Ku = d_K1;
+        if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy2D"));
+        c->v.kind = CCB_CTRL_LQR_INF; c->v.N = 0; c->v.K_bs = S > 1 ? (long long)row : 0;
+    } else {
+        c->v.kind = CCB_CTRL_LQR_FIN; c->v.N = N; c->v.K_bs = S > 1 ? (long long)(rows_all * row) : 0;
+    }
+    c->allocs.push_back(d_Ku);
+    c->v.K = d_Ku;
+    d_Ku = nullptr;
+    void *p_eqc = nullptr, *p_zd = nullptr, *p_Fd = nullptr;
+    if (cudaMalloc(&p_eqc, nu * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_eqc);
+    if (cudaMalloc(&p_zd, (size_t)S * nb * 13 * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_zd);
+    if (cudaMalloc(&p_Fd, (size_t)S * nu * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_Fd);
+    if (cudaMemcpy(p_eqc, eqc, nu * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_zd, zd, (size_t)S * nb * 13 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_Fd, Fd, (size_t)S * nu * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
+    c->v.eqc = (const int*)p_eqc;
+    c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)nb * 13 : 0;
+    c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)nu : 0;
+    *out = c;
+    return CCB_OK;
+}
+
+int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count) {
+    if (!c || !K || !c->v.K) { set_error("ccb_ctrl_get_gains: controller has no gain table"); return CCB_E_INVALID; }
+    const int64_t rows = c->v.kind == CCB_CTRL_LQR_INF ? 1 : (int64_t)c->v.N - 1;
+    const int64_t have = (c->v.K_bs ? (int64_t)c->B : 1) * rows * c->v.nu * n;
+    if (count != have) { set_error("ccb_ctrl_get_gains: the table holds " + std::to_string(have) + " doubles"); return CCB_E_INVALID; }
+    CCB_CUDA(cudaSetDevice(c->device));
+    CCB_CUDA(cudaMemcpy(K, c->v.K, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
     return CCB_OK;
 }
 

@@ -192,6 +192,16 @@ int ccb_lqr_synthesize(ccb_mech* m, int32_t device, int32_t S, const double* zd,
                        const double* Q, int64_t Q_bstride, const double* R, int64_t R_bstride, int32_t N, const ccb_sim_opts* opts,
                        double* Ku, int32_t* kexit, int32_t* iters);
 
+/* The same constructor with the gain table kept on the device: synthesis + ccb_ctrl_create in one call, nothing but the
+ * iteration counters comes back to the host.  infinite != 0: N is Ntemp = ceil(10/Δt), only Ku[1] is kept (lqr.jl:26,42) and
+ * converged[s] (may be NULL) = (Ku[1] == Ku[2]) (lqr.jl:41); infinite == 0: control_lqr! for k < N (lqr.jl:106).
+ * The controller is laid out for S systems (S == 1: shared by every system of any batch). */
+int ccb_lqr_create(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu, const double* Q,
+                   int64_t Q_bstride, const double* R, int64_t R_bstride, int32_t N, int32_t infinite, const ccb_sim_opts* opts, ccb_ctrl** out,
+                   int32_t* kexit, int32_t* iters, int32_t* converged);
+/* copy the gain table of an LQR / TrackingLQR controller to the host: [B or 1][rows][nu][n]; count = number of doubles expected */
+int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count);
+
 /* dlqr(mechanism, xd, vd, qd, ωd, Fτd, eqcids, Q, R, N)  (reference src/control/lqr_tracking.jl:73-122) for S
  * reference trajectories: traj [S][N][nb][13], Ftau [S][N][nu]; Ku [S][N-1][nu][n]. */
 int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,

@@ -104,3 +104,28 @@ def test_tracking_lqr_triple_cartpole(cc, orc):
     r = om.simulate(st0, N, ctrl=ctrl_o, record=True)
     out, final, _ = cc.simulate(mech, N * mech.dt, tl, record=True, states=st0, return_status=True)
     assert rel_err(out.data, r["storage"]) < 1e-8
+
+
+def test_lqr_per_system_setpoints_device_resident(cc, orc):
+    # LQR(...) with one setpoint per system: gains synthesised and kept on the device (ccb_lqr_create), rollout vs the oracle
+    mech, cfg = cc.examples.cartpole()
+    S = 4
+    ys = np.array([-0.3, 0.0, 0.2, 0.45])
+    xd = np.zeros((S, 2, 3)); xd[:, 0, 1] = ys; xd[:, 1, 1] = ys; xd[:, 1, 2] = 0.5
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], 2.0, xd=xd)
+    assert lqr.K.shape == (S, 199, 1, 24)
+    om = orc.OracleMech(mech.desc())
+    Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
+    st0 = cartpole_states(cc, mech, S, seed=5)
+    for s in range(S):
+        lin = om.linearize(lqr.zd[s], [0.0], [0])
+        ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd, Rd, 200)
+        assert rel_err(lqr.K[s], ref["Ku"]) < TOL
+        ctrl_o = om.make_ctrl(1, kind="lqr_finite", eqc=[0], N=200, K=ref["Ku"], zd=lqr.zd[s], Fd=np.zeros(1))
+        r = om.simulate(st0[s:s + 1], 250, ctrl=ctrl_o, record=True)
+        if s == 0:
+            refs = np.zeros((250, S, 2, 13))
+        refs[:, s] = r["storage"][:, 0]
+    storage, final, status = cc.simulate(mech, 2.5, lqr, record=True, states=st0, return_status=True)
+    assert np.all(status > 0)
+    assert rel_err(storage.data, refs) < TOL
