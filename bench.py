@@ -103,6 +103,43 @@ def gains_for(cc, mech, cfg, horizon):
     return lqr, "gpu"
 
 
+def synthesis_bench(cc, torch, dev, peaks):
+    """LQR syntheses/s (the second half of BASELINE.json's metric): batches of LQR(...) constructors with distinct weights.
+    device = CUDA-event time of linearsystem + projection + Riccati sweep (ccb_synth_phase_ms); e2e = wall time of the public
+    constructor with host inputs (H2D of setpoints/weights, gains stay on the device, iteration counters D2H)."""
+    out = {}
+    golden = os.path.join(ROOT, "tests", "golden", "sawyer_arm.json")
+    for name, S in (("cartpole", 4096), ("sawyer", 1024)):
+        mech, cfg = cc.examples.sawyer(golden) if name == "sawyer" else cc.examples.cartpole()
+        horizon = 20.0
+        nu, n = len(cfg["eqcids"]), 12 * mech.nb
+        rng = np.random.default_rng(2)
+        qs = np.exp(rng.uniform(np.log(0.1), np.log(10), S)); rs = np.exp(rng.uniform(np.log(0.1), np.log(10), S))
+        Qb = cc.blockdiag(cfg["Q"])[None] * qs[:, None, None]; Rb = cc.blockdiag(cfg["R"])[None] * rs[:, None, None]
+        xd = cfg["xd"]
+        best = None
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], None, None, horizon, xd=xd, qd=cfg.get("qd"), Q_batch=Qb, R_batch=Rb, device=dev)
+            wall = time.time() - t0
+            ph = cc.synth.phase_ms()
+            if best is None or wall < best[0]:
+                best = (wall, ph, float(lqr.riccati_iters.mean()))
+            lqr.invalidate()
+        wall, ph, iters = best
+        dev_s = sum(ph.values()) * 1e-3
+        flops = S * iters * (4.0 * n ** 3 + 8.0 * nu * n * n)          # SURVEY 8(d): two n^3 products + the nu-row products per iteration
+        tf = flops / (ph["sweep"] * 1e-3) / 1e12
+        peak = peaks.get("dmma_m8n8k4_tflops")
+        out[name] = {"batch": S, "n": n, "nu": nu, "horizon_steps": int(math.ceil(horizon / mech.dt)), "riccati_iters_mean": iters,
+                     "syntheses_per_s_device": S / dev_s, "syntheses_per_s_e2e": S / wall, "phase_ms": ph,
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": (tf / peak) if peak else None,
+                                  "peak_source": "measured mma.sync.m8n8k4.f64 rate (tools/peaks.cu, profiles/fp64_peaks.json)",
+                                  "kernel": "riccati_sweep_dmma_kernel"}}
+    return out
+
+
 def cpu_reference_run(steps, warmup, sample_systems=None):
     """the reference arm / cpu_baseline: CPU restatement on all host cores, bounded sample of the same workload"""
     import ccb200 as cc
@@ -141,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the synthesis / large-batch extras (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,7 +298,7 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sim_steps": SIM_STEPS, "mechanism": "cartpole (2 bodies, 2 joints, m_lambda=10)",
                        "newton_eps": 1e-10, "gains": gain_src, "l2": "flushed (256 MB write) between timed iterations",
                        "parallelism": f"dp{world} (independent systems, no collective on the step path)",
-                       "lanes_per_system": args.lanes or cc.handle(mech).lanes},
+                       "kernel": "rollout_rows_kernel<2> (K1r: one lane per constraint row)" if args.lanes in (0, 5) else f"lanes={args.lanes}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = 2*8*(13*Nb+m_lambda) per system-step (SURVEY 8(d)); the fused kernel keeps state on chip, "
@@ -269,6 +307,39 @@ def main():
             "gpu_launches": launches, "clocks": sampler.summary(), "wall_s_timed_region": wall,
             "newton_iters_per_sim_step": float(status.mean() / SIM_STEPS),
         }
+        fp = {}
+        try:
+            fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks.json")))
+        except Exception:
+            pass
+        # FP64 view of the same kernel: useful flops per system-step counted from the executed FP64 thread instructions of the
+        # non-redundant one-lane-per-joint kernel K1c (profiles/k1c_v1_*: 24.6 kflop at 3.0 Newton iterations -> 8.2 kflop per iteration)
+        iters_per_step = float(status.mean() / SIM_STEPS)
+        flops_per_step = 8.2e3 * iters_per_step
+        tf = flops_per_step * BATCH * SIM_STEPS / per_launch_s / 1e12
+        out["roofline"]["fp64"] = {"achieved_tflops": tf, "peak_tflops": fp.get("dfma_peak_tflops"), "frac": (tf / fp["dfma_peak_tflops"]) if fp.get("dfma_peak_tflops") else None,
+                                   "flops_per_system_step": flops_per_step, "peak_source": "measured DFMA rate (tools/peaks.cu)"}
+        if world == 1 and not args.no_extras:
+            try:
+                out["synthesis"] = synthesis_bench(cc, torch, dev, fp)
+            except Exception as e:   # the headline line must still print
+                out["synthesis"] = {"error": repr(e)}
+            try:   # the same rollout kernel at a batch that fills the machine (north_star: ">= 4096-system batches")
+                Bbig = 16 * BATCH
+                big = cc.Batch(mech, Bbig, dev)
+                stb = np.tile(st0, (16, 1, 1))
+                ts = []
+                sb = torch.cuda.ExternalStream(big.stream(), device=dev)
+                for _ in range(3):
+                    big.set_state(stb)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(sb); big.simulate_device(lqr, 1, SIM_STEPS, lanes=args.lanes); e1.record(sb); e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                out["large_batch"] = {"batch": Bbig, "sim_steps": SIM_STEPS, "value": Bbig * SIM_STEPS / (min(ts) * 1e-3), "unit": "sim steps/s", "ms": min(ts)}
+                del big
+            except Exception as e:
+                out["large_batch"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference_run(1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "sim steps/s", "cores": cores, "kind": "port", "sample": sample}

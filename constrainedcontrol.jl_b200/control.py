@@ -240,14 +240,16 @@ class LQR(Controller):
     `LQR.from_gains` wraps gains that already exist (K [rows][nu][12 nb] or [S][rows][nu][12 nb])."""
 
     def __init__(self, mechanism: Mechanism, bodyids, eqcids, Q, R, horizon, xd=None, vd=None, qd=None, wd=None, Ftaud=None, device: int = 0,
-                 opts: Optional[dict] = None):
+                 opts: Optional[dict] = None, Q_batch=None, R_batch=None):
+        """Q_batch [S][12 nb][12 nb] / R_batch [S][nu][nu] (optional): one assembled weight matrix per system instead of the
+        shared block lists Q / R (a synthesis batch; they are scaled by Δt like lqr.jl:18-19)"""
         super().__init__()
         mech = mechanism
         nb = mech.nb
         # lqr.jl:59-60
-        if not (len(bodyids) == len(Q) == nb):
+        if not (len(bodyids) == nb and (Q_batch is not None or len(Q) == nb)):
             raise AssertionError("Missmatched length for bodies")
-        if not (len(eqcids) == len(R)) or (Ftaud is not None and np.asarray(Ftaud).reshape(-1, len(eqcids)).shape[-1] != len(eqcids)):
+        if not (R_batch is not None or len(eqcids) == len(R)) or (Ftaud is not None and np.asarray(Ftaud).reshape(-1, len(eqcids)).shape[-1] != len(eqcids)):
             raise AssertionError("Missmatched length for constraints")
         if [mech.body_index(i) for i in bodyids] != list(range(nb)):
             raise CcbError("bodyids must list the mechanism's bodies in order (Δz is indexed by body position, lqr.jl:91)")
@@ -257,12 +259,12 @@ class LQR(Controller):
         nu = len(eqcids)
         zd = _zd_array(nb, xd, vd, qd, wd)
         Fd = np.zeros((1, nu)) if Ftaud is None else f64(Ftaud).reshape(-1, nu)
-        S = max(zd.shape[0], Fd.shape[0])
+        S = max(zd.shape[0], Fd.shape[0], 1 if Q_batch is None else len(Q_batch), 1 if R_batch is None else len(R_batch))
         zd = np.broadcast_to(zd, (S, nb, 13)).copy()
         Fd = np.broadcast_to(Fd, (S, nu)).copy()
         dt = mech.dt
-        Qd = blockdiag(Q) * dt            # lqr.jl:18
-        Rd = blockdiag(R) * dt            # lqr.jl:19
+        Qd = blockdiag(Q) * dt if Q_batch is None else f64(Q_batch) * dt            # lqr.jl:18
+        Rd = blockdiag(R) * dt if R_batch is None else f64(R_batch) * dt            # lqr.jl:19
         N = horizon / dt                  # lqr.jl:21-27
         if N < math.inf:
             N = int(math.ceil(horizon / dt))
