@@ -302,6 +302,30 @@ class Mechanism:
         for b, r in zip(self.bodies, s):
             b.state.xc, b.state.qc, b.state.vc, b.state.wc = r[0:3].copy(), r[3:7].copy(), r[7:10].copy(), r[10:13].copy()
 
+    def constraint_values(self) -> np.ndarray:
+        """position-level joint residuals g(xc, qc) of every joint, concatenated: translational part
+        R_a^T (x_b + R_b p2 - x_a) - p1 and rotational part vec(q_a^-1 q_b q_off^-1), each restricted to the constrained
+        directions (all 3; the 2 orthogonal to the axis; or the axis).  A host-side diagnostic, not used by any solver."""
+        out = []
+        for e in self.eqconstraints:
+            for j in e.constraints:
+                if isinstance(j.parent, Origin):
+                    xa, qa = np.zeros(3), ONE_Q
+                else:
+                    xa, qa = j.parent.state.xc, j.parent.state.qc
+                xb, qb = j.child.state.xc, j.child.state.qc
+                ax = j.axis / (np.linalg.norm(j.axis) or 1.0)
+                gT = qrot(qconj(qa), xb + qrot(qb, j.p2) - xa) - j.p1
+                gR = qmul(qmul(qconj(qa), qb), qconj(j.qoffset))[1:4]
+                for n, g in ((j.nT, gT), (j.nR, gR)):
+                    if n == 3:
+                        out.append(g)
+                    elif n == 2:
+                        out.append(g - np.dot(ax, g) * ax)
+                    elif n == 1:
+                        out.append(np.array([np.dot(ax, g)]))
+        return np.concatenate(out) if out else np.zeros(0)
+
     def batch_states(self, B: int) -> np.ndarray:
         """[B][nb][13], every system initialised from the bodies' current states"""
         return np.repeat(self.state_vector()[None], B, axis=0).copy()

@@ -1,28 +1,30 @@
 import sys, math, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/oracle'); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc, orc
-from helpers import rel_err, zd_of
-mech, cfg = cc.examples.sawyer('/root/repo/tests/golden/sawyer_arm.json')
+from helpers import rel_err
+mech, cfg = cc.examples.doublependulum()
+n = 32
+g1, g2 = np.meshgrid(np.linspace(-math.pi, math.pi, n, endpoint=False), np.linspace(-math.pi, math.pi, n, endpoint=False))
+goals = np.stack([g1.ravel(), g2.ravel()], axis=1)
+B = goals.shape[0]
+st0 = mech.batch_states(B)
+for lanes in (0, 1, 8):
+    pid = cc.PID(mech, cfg["eqcids"], goals, P=cfg["P"], I=cfg["I"], D=cfg["D"])
+    sto, fin, status = cc.simulate(mech, 10.0, pid, record=False, states=st0, return_status=True, lanes=lanes)
+    bad = np.where(status <= 0)[0]
+    print("lanes", lanes, "failed", len(bad), bad[:10], "iters/step", np.abs(status).mean() / 1000)
 om = orc.OracleMech(mech.desc())
-eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
-zd = zd_of(mech, cfg)
-Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
-N = 2000
-out = cc.lqr_synthesize(mech, zd[None], np.zeros((1, 7)), eqc_idx, Qd, Rd, N)
-K = out["Ku"][0]
-print('K max', np.abs(K).max(), 'kexit', out['kexit'], 'iters', out['iters'])
-lqr = cc.LQR.from_gains(mech, cfg["eqcids"], K, N, xd=zd[:, 0:3], qd=zd[:, 3:7])
-for amp in (0.05, 0.01, 0.002):
-    rng = np.random.default_rng(3)
-    B = 32
-    st = np.zeros((B, mech.nb, 13))
-    for s in range(B):
-        cc.urdf.zero_configuration(mech, {i: rng.uniform(-amp, amp) for i in range(7)})
-        st[s] = mech.state_vector()
-    co = om.make_ctrl(B, kind="lqr_finite", eqc=eqc_idx, N=N, K=K, zd=zd, Fd=np.zeros(7))
-    steps = 300
-    r = om.simulate(st, steps, ctrl=co, record=True, nthreads=8)
-    sto, fin, status = cc.simulate(mech, steps * mech.dt, lqr, record=True, states=st, return_status=True)
-    print('amp', amp, 'oracle fails', int((r['iters'] <= 0).sum()), 'gpu fails', int((status <= 0).sum()), 'mean iters', np.abs(r['iters']).mean()/steps, np.abs(status).mean()/steps)
-    ok = (r['iters'] > 0) & (status > 0)
-    if ok.any(): print('   parity on converged systems', rel_err(sto.data[:, ok], r['storage'][:, ok]), 'final dev from setpoint', np.abs(fin[ok][:, :, 0:3] - zd[:, 0:3]).max())
+eqc = [mech.eqc_index(i) for i in cfg["eqcids"]]
+sub = np.concatenate([bad[:8], np.arange(0, B, 128)])
+integ = np.zeros((len(sub), 2)); last = np.zeros((len(sub), 2))
+co = om.make_ctrl(len(sub), kind="pid", eqc=eqc, P=cfg["P"], I=cfg["I"], D=cfg["D"], goal=goals[sub], pid_int=integ, pid_last=last)
+r = om.simulate(st0[sub], 1000, ctrl=co, record=True, nthreads=8)
+print("oracle iters", r["iters"])
+pid2 = cc.PID(mech, cfg["eqcids"], goals[sub], P=cfg["P"], I=cfg["I"], D=cfg["D"])
+sto2, fin2, st2 = cc.simulate(mech, 10.0, pid2, record=True, states=st0[sub], return_status=True)
+print("gpu status", st2)
+for i in range(len(sub)):
+    e = np.abs(sto2.data[:, i] - r["storage"][:, i]).max(axis=(1, 2))
+    first = np.argmax(e > 1e-8) if (e > 1e-8).any() else -1
+    print(i, sub[i], goals[sub[i]], "max err", e.max(), "first step >1e-8:", first, "max |w|", np.abs(r["storage"][:, i, :, 10:13]).max())
