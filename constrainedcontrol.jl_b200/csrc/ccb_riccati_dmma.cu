@@ -73,6 +73,12 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         it++;
         const double* Ak = At + s * stride_s_A + (size_t)(k - 1) * stride_t_A;
         const double* Dk = D + s * stride_s_D + (size_t)(k - 1) * stride_t_D;
+        if (stride_t_A != 0 && k > 1) {   // time-varying (TrackingLQR): pull the next step's Ã, D into L2 while this step computes
+            const char* pa = reinterpret_cast<const char*>(Ak - stride_t_A);
+            for (size_t off = (size_t)tid * 128; off < nn * sizeof(double); off += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
+            const char* pd = reinterpret_cast<const char*>(Dk - stride_t_D);
+            for (size_t off = (size_t)tid * 128; off < (size_t)n * nu * sizeof(double); off += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + off));
+        }
         if (it == 1 || stride_t_D != 0) {
             for (int e = tid; e < n * 8; e += NT) { const int i = e >> 3, j = e & 7; Dp[e] = j < nu ? Dk[(size_t)i * nu + j] : 0.0; }
             __syncthreads();

@@ -283,9 +283,13 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
     CCB_TRY(check_device(device, "ccb_tracking_synthesize"));
     const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
     // every (trajectory, k) linearisation is independent (lqr_tracking.jl:88); only Pk carries the recursion.
-    // Chunk over trajectories so that the per-chunk matrices stay below ~6 GB.
-    const size_t per_traj = (size_t)N * ((size_t)2 * n * n + 2 * (size_t)n * nu + 2 * (size_t)n * ml) * sizeof(double);
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)6 << 30) / std::max<size_t>(per_traj, 1)));
+    // Chunk over trajectories so that the per-chunk matrices use at most half of the free HBM (180 GB per B200), in equal chunks.
+    const size_t per_traj = (size_t)N * ((size_t)2 * n * n + 2 * (size_t)n * nu + 2 * (size_t)n * ml + 2 * (size_t)ml * (ml + n + nu)) * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    CCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (free_b / 2) / std::max<size_t>(per_traj, 1)));
+    const int passes = (S + chunk - 1) / chunk;
+    chunk = (S + passes - 1) / passes;
     Scratch sc;
     double *d_Q, *d_R;
     int* d_eqc;

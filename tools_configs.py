@@ -107,3 +107,29 @@ if want("C4"):
         cc.urdf.zero_configuration(mech)
         return out
     run_lqr_config("C4 lqr_sawyer", mech, cfg, st_fn, 1024, 2000, 20.0, parity_steps=100, synth_S=64)
+if want("C5a"):
+    # lqr_deltabot: closed chain (2 loops, rank-deficient constraint set); gravity-compensating feed-forward, horizon Inf
+    mech, cfg = cc.examples.deltabot()
+    def st_fn(B):
+        rng = np.random.default_rng(5)
+        st = mech.batch_states(B)
+        return st
+    try:
+        run_lqr_config("C5 lqr_deltabot", mech, cfg, st_fn, 2048, 1000, math.inf, parity_B=4, parity_steps=100, synth_S=64)
+    except Exception as e:
+        print(json.dumps(dict(config="C5 lqr_deltabot", error=repr(e))), flush=True)
+if want("C5b"):
+    mech, cfg = cc.examples.doublependulum()
+    n = 32
+    g1, g2 = np.meshgrid(np.linspace(-math.pi, math.pi, n, endpoint=False), np.linspace(-math.pi, math.pi, n, endpoint=False))
+    goals = np.stack([g1.ravel(), g2.ravel()], axis=1)
+    B = goals.shape[0]
+    st0 = mech.batch_states(B)
+    pid = cc.PID(mech, cfg["eqcids"], goals, P=cfg["P"], I=cfg["I"], D=cfg["D"])
+    batch = cc.Batch(mech, B)
+    def go():
+        batch.set_state(st0)
+        return batch.simulate(pid, 1, 1000)
+    t, (_, status) = timed(go)
+    print(json.dumps(dict(config="C5 pid_doublependulum 32x32 goal sweep", B=B, steps=1000, rollout_s=t, sim_steps_per_s=B * 1000 / t,
+                          newton_per_step=float(np.abs(status).mean() / 1000), flagged=int((status <= 0).sum()))), flush=True)
