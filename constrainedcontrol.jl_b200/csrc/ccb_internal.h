@@ -138,13 +138,16 @@ struct SimArgs {
 };
 
 // lanes: 0 = automatic (row-per-lane kernel K1r for short serial chains, else the chain kernel K1c for serial chains, else the
-// general kernel K1 with default_lanes), 5 = force K1r, 1 = force K1c, 8/16/32 = K1 with that many lanes per system
+// multi-warp rows kernel K1m for longer serial chains, else the general kernel K1 with default_lanes), 5 = force K1r, 6 = force K1m,
+// 1 = force K1c, 8/16/32 = K1 with that many lanes per system
 int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, int default_lanes, cudaStream_t stream);
 bool chain_tables(const HostMech& H, std::vector<int>& parent, std::vector<int>& child, std::vector<int>& depth, int& max_depth, int& max_dim);
 int launch_rollout_chain(const DevMech& M, const DevCtrl& C, const SimArgs& a, const int* d_parent, const int* d_child, const int* d_depth,
                          int max_depth, int max_dim, cudaStream_t stream);
 int rollout_smem_bytes(const DevMech& M, int lanes);
 int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
+bool mw_kernel_eligible(const DevMech& M);
+int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
 
 }  // namespace ccb
 

@@ -519,11 +519,13 @@ int rollout_smem_bytes(const DevMech& M, int lanes) { return (32 / lanes) * M.sm
 int launch_rollout(const DevMech& M, const DevCtrl& C, const SimArgs& a, int lanes, int default_lanes, cudaStream_t stream) {
     if ((lanes == 0 || lanes == 5) && M.rows_ok) return launch_rollout_rows(M, C, a, stream);
     if (lanes == 5) { set_error("lanes = 5 (row-per-lane kernel) needs a single serial chain of <= 6 joints of dimension <= 5"); return CCB_E_INVALID; }
-    if ((lanes == 0 || lanes == 1) && M.is_chain)
+    if ((lanes == 0 || lanes == 6) && mw_kernel_eligible(M)) return launch_rollout_mw(M, C, a, stream);
+    if (lanes == 6) { set_error("lanes = 6 (multi-warp rows kernel) needs a single serial chain with joints of dimension <= 5"); return CCB_E_INVALID; }
+    if ((lanes == 0 || lanes == 1) && M.is_chain && M.nj <= 32)
         return launch_rollout_chain(M, C, a, M.chain_parent, M.chain_child, M.chain_depth, M.chain_max_depth, M.chain_max_dim, stream);
     if (lanes == 1) { set_error("lanes = 1 (chain kernel) requested for a mechanism that is not a serial chain"); return CCB_E_INVALID; }
     if (lanes == 0) lanes = default_lanes;
-    if (lanes != 8 && lanes != 16 && lanes != 32) { set_error("lanes per system must be 0 (auto), 5 (row-per-lane kernel), 1 (chain kernel), 8, 16 or 32"); return CCB_E_INVALID; }
+    if (lanes != 8 && lanes != 16 && lanes != 32) { set_error("lanes per system must be 0 (auto), 5 (row-per-lane kernel), 6 (multi-warp rows kernel), 1 (chain kernel), 8, 16 or 32"); return CCB_E_INVALID; }
     const int per_cta = 32 / lanes;
     const int grid = (a.B + per_cta - 1) / per_cta;
     const size_t smem = (size_t)rollout_smem_bytes(M, lanes);

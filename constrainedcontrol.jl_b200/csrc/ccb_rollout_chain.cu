@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(32) rollout_chain_kernel(const DevMech M, cons
 // Eligibility + tables for the chain kernel: every eqc holds one joint, every body is the child of exactly one joint and
 // the parent of at most one, eqc e's joint is joint e, at most 32 joints.
 bool chain_tables(const HostMech& H, std::vector<int>& parent, std::vector<int>& child, std::vector<int>& depth, int& max_depth, int& max_dim) {
-    if (H.nj != H.ne || H.nj != H.nb || H.nj > 32 || H.nj < 1) return false;
+    if (H.nj != H.ne || H.nj != H.nb || H.nj < 1) return false;   // (K1c itself needs nj <= 32: checked at launch)
     std::vector<int> joint_of_body(H.nb, -1), kids(H.nb, 0);
     max_dim = 0;
     for (int j = 0; j < H.nj; j++) {

@@ -151,7 +151,8 @@ typedef struct ccb_sim_opts {
     double eps;           /* newton! ε, default 1e-10 */
     int32_t newton_iter;  /* default 100 */
     int32_t line_iter;    /* default 10 */
-    int32_t lanes;        /* 0 = automatic (serial chains: one lane per joint+body), 1 = force the chain kernel, 8/16/32 = general kernel */
+    int32_t lanes;        /* kernel choice: 0 = automatic; 5 = K1r (one lane per constraint row, <= 6 joints); 6 = K1m (same, one CTA per
+                             system, long chains); 1 = K1c (one lane per joint); 8/16/32 = general kernel K1 with that many lanes */
     int32_t reserved;     /* chain kernel: systems per warp, 0 = automatic (tuning knob) */
 } ccb_sim_opts;
 

@@ -56,12 +56,10 @@ def test_c3_npendulum8_rollout_and_gains(cc, orc):
     co = om.make_ctrl(B, kind="lqr_finite", eqc=eqc_idx, N=300, K=K, zd=zd, Fd=np.zeros(1))
     r = om.simulate(st0, 150, ctrl=co, record=True, nthreads=8)
     lqr = cc.LQR.from_gains(mech, cfg["eqcids"], K, 300, xd=zd[:, 0:3])
-    sto, fin, status = cc.simulate(mech, 1.5, lqr, record=True, states=st0, return_status=True)
-    assert np.all(status > 0)
-    assert rel_err(sto.data, r["storage"]) < TOL
-    # the general kernel (K1, 32 lanes) on the same problem
-    sto2, fin2, status2 = cc.simulate(mech, 1.5, lqr, record=True, states=st0, lanes=32, return_status=True)
-    assert rel_err(sto2.data, r["storage"]) < TOL
+    for lanes in (0, 6, 1, 32):      # automatic (= K1m, one CTA per system), K1m, K1c (one lane per joint), general K1
+        sto, fin, status = cc.simulate(mech, 1.5, lqr, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        assert rel_err(sto.data, r["storage"]) < TOL, lanes
 
 
 def test_c3_npendulum32_tree_solve(cc, orc):
@@ -75,10 +73,12 @@ def test_c3_npendulum32_tree_solve(cc, orc):
     B = 4
     st0 = chain_states(cc, mech, B, 3, 0.05)
     r = om.simulate(st0, 40, record=True, nthreads=4)
-    sto, fin, status = cc.simulate(mech, 0.4, None, record=True, states=st0, return_status=True)
-    assert np.all(status > 0) and np.all(r["iters"] > 0)
-    assert rel_err(sto.data, r["storage"]) < TOL
-    assert constraint_violation(cc, mech, fin) < 1e-9
+    assert np.all(r["iters"] > 0)
+    for lanes in (0, 32):            # K1m (6 warps per system) and the general kernel
+        sto, fin, status = cc.simulate(mech, 0.4, None, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        assert rel_err(sto.data, r["storage"]) < TOL, lanes
+        assert constraint_violation(cc, mech, fin) < 1e-9
     # linearsystem at the upright setpoint (n = 396): block-sparse K2 vs the oracle's whole-residual AD
     eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
     zd = zd_of(mech, cfg)
@@ -113,10 +113,11 @@ def test_c4_sawyer_lqr_and_rollout(cc, orc):
     st0 = sawyer_states(cc, mech, B, 3, 0.01)
     co = om.make_ctrl(B, kind="lqr_finite", eqc=eqc_idx, N=N, K=ref["Ku"], zd=zd, Fd=np.zeros(7))
     r = om.simulate(st0, 120, ctrl=co, record=True, nthreads=8)
-    sto, fin, status = cc.simulate(mech, 1.2, lqr, record=True, states=st0, return_status=True)
-    assert np.all(status > 0)
-    assert rel_err(sto.data, r["storage"]) < TOL
-    assert constraint_violation(cc, mech, fin) < 1e-9
+    for lanes in (0, 1):             # K1m and K1c
+        sto, fin, status = cc.simulate(mech, 1.2, lqr, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        assert rel_err(sto.data, r["storage"]) < TOL, lanes
+        assert constraint_violation(cc, mech, fin) < 1e-9
 
 
 def test_c4_sawyer_tracking(cc, orc):
