@@ -429,8 +429,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         // S dλ = rhs with one row per lane.  Elimination runs from the last row of the leaf joint to the first row of the
         // root joint, so a pivot row only has entries to its left (parent block + own block) and the rows it updates are the
         // earlier rows of its own block and the rows of the parent block: no fill.  On exit `rhs` holds dλ.
-        double dl = 0.0, ds[6];
-        auto solve = [&]() {
+        auto solve = [&](double& dl, double* ds) {
             double myinv = 1.0;
 #pragma unroll
             for (int pp = NJ - 1; pp >= 0; pp--) {
@@ -484,61 +483,67 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             ds[3] = dw.x; ds[4] = dw.y; ds[5] = dw.z;
         };
 
-        bool done = !valid;
-        double normf0 = 0.0;
-        int it_used = 0;
-        for (int n = 1; n <= A.newton_iter; n++) {
-            if (__all_sync(0xffffffffu, done)) break;
-            const bool act = !done;
-            const double nf = evaluate(true);
-            if (n == 1) normf0 = nf;
-            solve();
-            double sd = dl * dl;
-            if (r == 0) {
+        // newton! / lineSearch! as one loop around a single evaluation site.  The residual at an accepted line-search point is the
+        // residual the next Newton iteration starts from, so every evaluation also forms the Jacobian rows: an iteration costs one
+        // evaluation + one solve (instead of evaluation + solve + line-search evaluation), the iterates are unchanged.
+        bool done = !valid, pending = false, first = true, out_of_iters = false;
+        int n = 0, ls = 0;
+        double alpha = 1.0, full = 0.0, normf0 = 0.0, lam0 = lam;
+        double s0[6];
 #pragma unroll
-                for (int i = 0; i < 6; i++) sd = fma(ds[i], ds[i], sd);
-            }
-            if (!valid) sd = 0.0;
-            const double full = sqrt(sys_sum(sd));
-            double s0[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) s0[i] = s[i];
-            const double lam0 = lam;
-            // a step below eps taken from a residual below eps ends the solve whatever scale the line search would pick
-            const bool tiny = act && full < A.eps && normf0 < A.eps;
-            double alpha = 1.0, normf1 = normf0;
-            bool ls_done = !act || tiny;
-            if (tiny) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
-                lam = lam0 - dl;
-            }
-            for (int ls = 0; ls <= A.line_iter; ls++) {      // lineSearch!: s = s_prev - 2^-j step, first j with |f| decreased
-                if (__all_sync(0xffffffffu, ls_done)) break;
-                const bool la = !ls_done;
-                if (la) {
+        for (int i = 0; i < 6; i++) s0[i] = s[i];
+        double dl = 0.0, ds[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (;;) {
+            const double nfe = evaluate(true);
+            bool want_solve = false;
+            if (first) {
+                normf0 = nfe;
+                want_solve = !done;
+            } else if (pending) {
+                if (nfe >= normf0 && ls < A.line_iter) {          // lineSearch!: not decreased -> halve the step and try again
+                    alpha *= 0.5; ls++;
 #pragma unroll
                     for (int i = 0; i < 6; i++) s[i] = fma(-alpha, ds[i], s0[i]);
                     lam = fma(-alpha, dl, lam0);
-                }
-                const double nf1 = evaluate(false);
-                if (la) {
-                    normf1 = nf1;
-                    if (nf1 >= normf0 && ls < A.line_iter) alpha *= 0.5;
-                    else ls_done = true;
+                } else {                                          // accepted (or out of halvings)
+                    pending = false;
+                    if (alpha * full < A.eps && nfe < A.eps) done = true;
+                    normf0 = nfe;
+                    if (!done && n >= A.newton_iter) { done = true; out_of_iters = true; }
+                    want_solve = !done;
                 }
             }
-            if (act) {
-                it_used = n;
-                const double nd = alpha * full;
-                if (tiny || (nd < A.eps && normf1 < A.eps)) done = true;
-                normf0 = normf1;
-            } else {   // a finished system keeps its solution while the other systems of the warp iterate
+            first = false;
+            if (!__any_sync(0xffffffffu, want_solve)) {
+                if (!__any_sync(0xffffffffu, pending)) break;
+                continue;
+            }
+            double dl_new, ds_new[6];
+            solve(dl_new, ds_new);
+            double sd = dl_new * dl_new;
+            if (r == 0) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) s[i] = s0[i];
-                lam = lam0;
+                for (int i = 0; i < 6; i++) sd = fma(ds_new[i], ds_new[i], sd);
             }
+            if (!valid) sd = 0.0;
+            const double fullv = sqrt(sys_sum(sd));
+            if (want_solve) {
+                n++;
+                full = fullv; dl = dl_new; lam0 = lam;
+#pragma unroll
+                for (int i = 0; i < 6; i++) { ds[i] = ds_new[i]; s0[i] = s[i]; }
+                alpha = 1.0; ls = 0;
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
+                lam = lam0 - dl;
+                // a step below eps taken from a residual below eps ends the solve whatever scale the line search would pick
+                if (full < A.eps && normf0 < A.eps) done = true;
+                else pending = true;
+            }
+            if (!__any_sync(0xffffffffu, pending)) break;
         }
+        const int it_used = n;
+        if (out_of_iters) done = false;
         if (valid) {
             total_iters += it_used;
             if (!done) failed = true;
