@@ -184,6 +184,15 @@ class Controller:
             self._dev[key] = (h, keep)
         return self._dev[key][0]
 
+    def replicate(self, per_table: int):
+        """let `per_table` consecutive systems of the batch share one gain table / desired trajectory (device-resident controllers)"""
+        nat = getattr(self, "_native", None)
+        if nat is None:
+            raise CcbError("replicate() needs a controller synthesised on the device")
+        check(_lib.lib().ccb_ctrl_set_replication(nat[0], C.c_int32(per_table)))
+        self._per_table = int(per_table)
+        return self
+
     def invalidate(self):
         for h, _ in self._dev.values():
             _lib.lib().ccb_ctrl_destroy(h)
@@ -307,7 +316,7 @@ class LQR(Controller):
 
     def device_handle(self, B: int, device: int):
         nat = getattr(self, "_native", None)
-        if nat is not None and nat[2] == device and nat[1] in (1, B):
+        if nat is not None and nat[2] == device and (nat[1] == 1 or nat[1] * getattr(self, "_per_table", 1) == B):
             return nat[0]
         return super().device_handle(B, device)
 
@@ -364,11 +373,47 @@ class TrackingLQR(Controller):
         Ft = np.broadcast_to(Ft, (S, N, nu)).copy()
         Qd = blockdiag(Q) * mech.dt       # lqr_tracking.jl:22-23
         Rd = blockdiag(R) * mech.dt
-        from .synth import tracking_synthesize
-        res = tracking_synthesize(mech, traj, Ft, self.eqc_idx, Qd, Rd, device=device, **(opts or {}))
-        self.K, self.kexit, self.riccati_iters = res["Ku"], res["kexit"], res["iters"]
+        # synthesis + controller tables in one C-ABI call: gains, desired trajectory and feed-forward stay on the device
+        from .synth import _opts
+        mh = handle(mech)
+        self.kexit = np.empty(S, np.int32); self.riccati_iters = np.empty(S, np.int32)
+        o = _opts(**(opts or {}))
+        h = C.c_void_p()
+        Qd, Rd = f64(Qd).reshape(mh.n, mh.n), f64(Rd).reshape(nu, nu)
+        check(_lib.lib().ccb_tracking_create(mh.h, C.c_int32(device), C.c_int32(S), C.c_int32(N), ptr(traj), ptr(Ft), ptr(self.eqc_idx), C.c_int32(nu),
+                                             ptr(Qd), ptr(Rd), C.byref(o), C.byref(h), ptr(self.kexit), ptr(self.riccati_iters)))
+        self._native = (h, S, device)
+        self._K = None
         self.N, self.zd, self.Fd = N, traj, Ft
         self.kind = CTRL_TRACKING
+
+    @property
+    def K(self):
+        """gain tables [S][N-1][nu][12 nb]; fetched from the device on first use"""
+        if self._K is None:
+            h, S, _ = self._native
+            n, nu = 12 * self.mech.nb, len(self.eqcids)
+            K = np.empty((S, self.N - 1, nu, n))
+            check(_lib.lib().ccb_ctrl_get_gains(h, C.c_int32(n), ptr(K), C.c_int64(K.size)))
+            self._K = K
+        return self._K
+
+    @K.setter
+    def K(self, v):
+        self._K = v
+
+    def device_handle(self, B: int, device: int):
+        nat = getattr(self, "_native", None)
+        if nat is not None and nat[2] == device and (nat[1] == 1 or nat[1] * getattr(self, "_per_table", 1) == B):
+            return nat[0]
+        return super().device_handle(B, device)
+
+    def invalidate(self):
+        nat = getattr(self, "_native", None)
+        if nat is not None:
+            _lib.lib().ccb_ctrl_destroy(nat[0])
+            self._native = None
+        super().invalidate()
 
     @classmethod
     def from_gains(cls, mechanism: Mechanism, eqcids, K, traj, Ftau):
@@ -379,6 +424,7 @@ class TrackingLQR(Controller):
         self.eqc_idx = i32([mechanism.eqc_index(i) for i in eqcids])
         traj = f64(traj)
         traj = traj.reshape(-1, traj.shape[-3], nb, 13)
+        self._native = None
         self.N = traj.shape[1]
         self.zd = traj
         self.Fd = f64(Ftau).reshape(-1, self.N, nu)

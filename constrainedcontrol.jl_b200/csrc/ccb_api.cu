@@ -190,6 +190,14 @@ int ccb_ctrl_destroy(ccb_ctrl* c) {
     delete c;
     return CCB_OK;
 }
+int ccb_ctrl_set_replication(ccb_ctrl* c, int32_t per_table) {
+    if (!c || per_table < 1) { set_error("ccb_ctrl_set_replication: bad arguments"); return CCB_E_INVALID; }
+    if (c->v.kind != CCB_CTRL_LQR_INF && c->v.kind != CCB_CTRL_LQR_FIN && c->v.kind != CCB_CTRL_TRACKING) {
+        set_error("ccb_ctrl_set_replication: only LQR / TrackingLQR controllers carry per-system tables"); return CCB_E_INVALID;
+    }
+    c->v.sys_div = per_table;
+    return CCB_OK;
+}
 int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t set) {
     if (!c || c->v.kind != CCB_CTRL_PID) { set_error("ccb_ctrl_pid_state: not a PID controller"); return CCB_E_INVALID; }
     CCB_CUDA(cudaSetDevice(c->device));
@@ -209,7 +217,9 @@ int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps,
                         int32_t* status_dev) {
     if (!b || steps < 0) { set_error("ccb_simulate: bad arguments"); return CCB_E_INVALID; }
     if (ctrl && ctrl->device != b->device) { set_error("ccb_simulate: controller lives on another device"); return CCB_E_INVALID; }
-    if (ctrl && ctrl->B != b->B && ctrl->B != 1) { set_error("ccb_simulate: controller tables were laid out for another batch size"); return CCB_E_INVALID; }
+    if (ctrl && ctrl->B != 1 && (long long)ctrl->B * (ctrl->v.sys_div > 1 ? ctrl->v.sys_div : 1) != b->B) {
+        set_error("ccb_simulate: controller tables were laid out for another batch size"); return CCB_E_INVALID;
+    }
     CCB_CUDA(cudaSetDevice(b->device));
     const DevMech* view;
     int rc = get_dev_mech(&b->mech->h, b->device, &view);

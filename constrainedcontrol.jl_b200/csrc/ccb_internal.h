@@ -122,6 +122,7 @@ struct DevCtrl {
     const double* goal; long long goal_bs;
     double* pid_int;
     double* pid_last;
+    int sys_div;        // LQR-type tables: system s uses table s / sys_div (0 or 1: one table per system or one shared table)
 };
 
 struct SimArgs {

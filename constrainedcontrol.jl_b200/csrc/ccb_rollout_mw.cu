@@ -193,17 +193,18 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
         {
             const int n = 12 * M.nb;
             bool lqr = false;
+            const int csys = C.sys_div > 1 ? sys / C.sys_div : sys;   // several systems may share one table (ccb_ctrl_set_replication)
             const double *K = nullptr, *zd = nullptr, *Fd = nullptr;
             if (C.kind == CCB_CTRL_LQR_INF) {
                 lqr = true;
-                K = C.K + (size_t)sys * C.K_bs; zd = C.zd + (size_t)sys * C.zd_bs; Fd = C.Fd + (size_t)sys * C.Fd_bs;
+                K = C.K + (size_t)csys * C.K_bs; zd = C.zd + (size_t)csys * C.zd_bs; Fd = C.Fd + (size_t)csys * C.Fd_bs;
             } else if (C.kind == CCB_CTRL_LQR_FIN) {
                 lqr = k < C.N;
-                K = C.K + (size_t)sys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)sys * C.zd_bs; Fd = C.Fd + (size_t)sys * C.Fd_bs;
+                K = C.K + (size_t)csys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)csys * C.zd_bs; Fd = C.Fd + (size_t)csys * C.Fd_bs;
             } else if (C.kind == CCB_CTRL_TRACKING) {
                 lqr = k < C.N;
-                K = C.K + (size_t)sys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)sys * C.zd_bs + (size_t)(k - 1) * 13 * M.nb;
-                Fd = C.Fd + (size_t)sys * C.Fd_bs + (size_t)(k - 1) * C.nu;
+                K = C.K + (size_t)csys * C.K_bs + (size_t)(k - 1) * C.nu * n; zd = C.zd + (size_t)csys * C.zd_bs + (size_t)(k - 1) * 13 * M.nb;
+                Fd = C.Fd + (size_t)csys * C.Fd_bs + (size_t)(k - 1) * C.nu;
             }
             if (lqr) {
                 V3 dz = {0.0, 0.0, 0.0};

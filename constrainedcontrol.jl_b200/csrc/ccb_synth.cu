@@ -276,11 +276,12 @@ int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count) {
     return CCB_OK;
 }
 
-int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
-                            int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku, int32_t* kexit, int32_t* iters) {
-    if (!m || S < 1 || N < 2 || !traj || !Ftau || nu < 1 || !eqc || !Q || !R || !Ku) { set_error("ccb_tracking_synthesize: bad arguments"); return CCB_E_INVALID; }
-    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_synthesize"));
-    CCB_TRY(check_device(device, "ccb_tracking_synthesize"));
+// TrackingLQR synthesis on the device for S trajectories.  Ku goes either to the host (Ku_host) or stays in d_Ku_all
+// ([S][N-1][nu][n], allocated by the caller); traj / Ftau are host arrays; d_traj_keep / d_F_keep (optional, device, whole
+// batch) receive copies of the desired trajectory and feed-forward for the controller.
+static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const double* traj, const double* Ftau, const int32_t* eqc, int nu,
+                                 const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku_host, double* d_Ku_all,
+                                 double* d_traj_keep, double* d_F_keep, int32_t* kexit, int32_t* iters) {
     const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
     // every (trajectory, k) linearisation is independent (lqr_tracking.jl:88); only Pk carries the recursion.
     // Chunk over trajectories so that the per-chunk matrices use at most half of the free HBM (180 GB per B200), in equal chunks.
@@ -294,14 +295,14 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
     double *d_Q, *d_R;
     int* d_eqc;
     CCB_TRY(sc.put(&d_Q, Q, (size_t)n * n)); CCB_TRY(sc.put(&d_R, R, (size_t)nu * nu)); CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
-    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_At, *d_D, *d_Ku, *d_ws1, *d_ws2;
+    double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_At, *d_D, *d_Ku = nullptr, *d_ws1, *d_ws2;
     int *d_status, *d_kexit, *d_iters;
     const size_t P = (size_t)chunk * N;
     CCB_TRY(sc.get(&d_zd, P * nb * 13)); CCB_TRY(sc.get(&d_Fd, P * nu));
     CCB_TRY(sc.get(&d_A, P * n * n)); CCB_TRY(sc.get(&d_Bu, P * n * nu)); CCB_TRY(sc.get(&d_Bl, P * n * ml)); CCB_TRY(sc.get(&d_G, P * ml * n));
     CCB_TRY(sc.get(&d_lam, P * ml)); CCB_TRY(sc.get(&d_s, P * nb * 6)); CCB_TRY(sc.get(&d_status, P));
     CCB_TRY(sc.get(&d_At, P * n * n)); CCB_TRY(sc.get(&d_D, P * n * nu));
-    CCB_TRY(sc.get(&d_Ku, (size_t)chunk * (N - 1) * nu * n));
+    if (!d_Ku_all) CCB_TRY(sc.get(&d_Ku, (size_t)chunk * (N - 1) * nu * n));
     CCB_TRY(sc.get(&d_ws1, P * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)chunk * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)chunk)); CCB_TRY(sc.get(&d_iters, (size_t)chunk));
@@ -309,8 +310,11 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
     for (int s0 = 0; s0 < S; s0 += chunk) {
         const int cs = std::min(chunk, S - s0);
         const int Pc = cs * N;
+        double* Kdst = d_Ku_all ? d_Ku_all + (size_t)s0 * (N - 1) * nu * n : d_Ku;
         CCB_CUDA(cudaMemcpy(d_zd, traj + (size_t)s0 * N * nb * 13, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
         CCB_CUDA(cudaMemcpy(d_Fd, Ftau + (size_t)s0 * N * nu, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
+        if (d_traj_keep) CCB_CUDA(cudaMemcpy(d_traj_keep + (size_t)s0 * N * nb * 13, d_zd, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyDeviceToDevice));
+        if (d_F_keep) CCB_CUDA(cudaMemcpy(d_F_keep + (size_t)s0 * N * nu, d_Fd, (size_t)Pc * nu * sizeof(double), cudaMemcpyDeviceToDevice));
         CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)Pc * ml, 1) * sizeof(double)));
         pt.mark(0);
         CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
@@ -318,14 +322,53 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
         CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
         pt.mark(2);
         CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
-                                     0, d_Ku, d_kexit, d_iters, d_ws2, 0));
+                                     0, Kdst, d_kexit, d_iters, d_ws2, 0));
         pt.mark(3);
         CCB_CUDA(cudaDeviceSynchronize());
         pt.finish(s0 > 0);
-        CCB_CUDA(cudaMemcpy(Ku + (size_t)s0 * (N - 1) * nu * n, d_Ku, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (Ku_host) CCB_CUDA(cudaMemcpy(Ku_host + (size_t)s0 * (N - 1) * nu * n, Kdst, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
         if (kexit) CCB_CUDA(cudaMemcpy(kexit + s0, d_kexit, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
         if (iters) CCB_CUDA(cudaMemcpy(iters + s0, d_iters, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
     }
+    return CCB_OK;
+}
+
+int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
+                            int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku, int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || N < 2 || !traj || !Ftau || nu < 1 || !eqc || !Q || !R || !Ku) { set_error("ccb_tracking_synthesize: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_synthesize"));
+    CCB_TRY(check_device(device, "ccb_tracking_synthesize"));
+    return tracking_synth_device(m, device, S, N, traj, Ftau, eqc, nu, Q, R, opts, Ku, nullptr, nullptr, nullptr, kexit, iters);
+}
+
+int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc, int32_t nu,
+                        const double* Q, const double* R, const ccb_sim_opts* opts, ccb_ctrl** out, int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || N < 2 || !traj || !Ftau || nu < 1 || !eqc || !Q || !R || !out) { set_error("ccb_tracking_create: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_create"));
+    CCB_TRY(check_device(device, "ccb_tracking_create"));
+    const int nb = m->h.nb, n = 12 * nb;
+    ccb_ctrl* c = new ccb_ctrl();
+    c->device = device; c->B = S;
+    std::memset(&c->v, 0, sizeof(c->v));
+    c->v.kind = CCB_CTRL_TRACKING; c->v.nu = nu; c->v.N = N;
+    auto fail = [&](int rc) { ccb_ctrl_destroy(c); return rc; };
+    void *pK = nullptr, *pz = nullptr, *pF = nullptr, *pe = nullptr;
+    if (cudaMalloc(&pK, (size_t)S * (N - 1) * nu * n * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(K)"));
+    c->allocs.push_back(pK);
+    if (cudaMalloc(&pz, (size_t)S * N * nb * 13 * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(zd)"));
+    c->allocs.push_back(pz);
+    if (cudaMalloc(&pF, (size_t)S * N * nu * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(Fd)"));
+    c->allocs.push_back(pF);
+    if (cudaMalloc(&pe, nu * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(eqc)"));
+    c->allocs.push_back(pe);
+    if (cudaMemcpy(pe, eqc, nu * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMemcpy(eqc)"));
+    int rc = tracking_synth_device(m, device, S, N, traj, Ftau, eqc, nu, Q, R, opts, nullptr, (double*)pK, (double*)pz, (double*)pF, kexit, iters);
+    if (rc != CCB_OK) return fail(rc);
+    c->v.eqc = (const int*)pe;
+    c->v.K = (const double*)pK; c->v.K_bs = S > 1 ? (long long)(N - 1) * nu * n : 0;
+    c->v.zd = (const double*)pz; c->v.zd_bs = S > 1 ? (long long)N * nb * 13 : 0;
+    c->v.Fd = (const double*)pF; c->v.Fd_bs = S > 1 ? (long long)N * nu : 0;
+    *out = c;
     return CCB_OK;
 }
 

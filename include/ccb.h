@@ -137,6 +137,9 @@ typedef struct ccb_ctrl ccb_ctrl;
 /* copies every table to `device`; host pointers are not retained */
 int ccb_ctrl_create(const ccb_mech* m, const ccb_ctrl_desc* desc, int32_t device, ccb_ctrl** out);
 int ccb_ctrl_destroy(ccb_ctrl* c);
+/* LQR / TrackingLQR controllers laid out for S tables: let `per_table` consecutive systems of a batch of S * per_table systems share
+ * table s / per_table (e.g. 16 perturbed initial states per reference trajectory) instead of replicating it */
+int ccb_ctrl_set_replication(ccb_ctrl* c, int32_t per_table);
 /* PID controller memory (`integratederrors`, `lasterrors`; pid.jl:9-10) [B][nu]; persists across simulate calls (pid.jl:76) */
 int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t set /* 0: read, 1: write */);
 
@@ -208,6 +211,12 @@ int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count);
 int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
                             int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku, int32_t* kexit,
                             int32_t* iters);
+
+/* TrackingLQR(mechanism, storage, Fτ, eqcids, Q, R) (lqr_tracking.jl:17-43) with the gain tables, the desired trajectories and the
+ * feed-forward kept on the device: synthesis + ccb_ctrl_create(CCB_CTRL_TRACKING) in one call.  The controller is laid out for S
+ * systems (S == 1: shared by every system of any batch); read the gains back with ccb_ctrl_get_gains. */
+int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc, int32_t nu,
+                        const double* Q, const double* R, const ccb_sim_opts* opts, ccb_ctrl** out, int32_t* kexit, int32_t* iters);
 
 /* Device time (ms, CUDA events on the launching stream) of the phases of the last ccb_dlqr / ccb_lqr_synthesize /
  * ccb_tracking_synthesize call on the calling thread: out[0] linearisation (K1 knot solve + K2), out[1] constraint projection,

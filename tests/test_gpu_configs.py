@@ -146,6 +146,19 @@ def test_c4_sawyer_tracking(cc, orc):
     out, fin, status = cc.simulate(mech, N * mech.dt, tl, record=True, states=st0, return_status=True)
     assert np.all(status > 0)
     assert rel_err(out.data, r["storage"]) < 1e-8
+    # two reference trajectories, two perturbed starts each: 4 systems share 2 device-resident tables (ccb_ctrl_set_replication)
+    U2 = np.stack([U, 0.5 * U])
+    mech.set_state_vector(st_init)
+    sto2, _, _ = cc.simulate(mech, N * mech.dt, cc.OpenLoop(mech, cfg["eqcids"], U2), record=True, states=mech.batch_states(2), return_status=True)
+    tl2 = cc.TrackingLQR(mech, sto2, U2, cfg["eqcids"], cfg["Q"], cfg["R"]).replicate(2)
+    assert rel_err(tl2.K[0], ref["Ku"]) < 1e-8
+    out2, _, status2 = cc.simulate(mech, N * mech.dt, tl2, record=True, states=st0, return_status=True)
+    assert np.all(status2 > 0)
+    for s in range(4):
+        t = s // 2
+        co = om.make_ctrl(1, kind="tracking", eqc=eqc_idx, N=N, K=tl2.K[t], zd=sto2.data[:, t], Fd=U2[t])
+        rr = om.simulate(st0[s:s + 1], N, ctrl=co, record=True)
+        assert rel_err(out2.data[:, s], rr["storage"][:, 0]) < 1e-8, s
 
 
 # ------------------------------------------------------------------------------------------------ C5: deltabot + PID sweep

@@ -31,8 +31,7 @@ pert = np.zeros((B, 7))
 for s in range(B):
     cc.urdf.zero_configuration(mech, {i: rng.uniform(-AMP, AMP) for i in range(7)})
     stp[s] = mech.state_vector()
-Kb = np.repeat(tl.K, PER, axis=0) if PER > 1 else tl.K
-trk = cc.TrackingLQR.from_gains(mech, cfg["eqcids"], Kb, np.repeat(tl.zd, PER, axis=0), np.repeat(tl.Fd, PER, axis=0))
+trk = tl.replicate(PER)      # 16 perturbed starts per reference trajectory share its (device-resident) tables
 batch = cc.Batch(mech, B)
 for rep in range(2):
     batch.set_state(stp)
