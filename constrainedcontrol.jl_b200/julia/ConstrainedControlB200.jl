@@ -12,7 +12,7 @@ using LinearAlgebra
 
 const libccb = get(ENV, "CCB_LIB", joinpath(@__DIR__, "..", "csrc", "libccb.so"))
 
-export BatchLQR, BatchTrackingLQR, BatchPID, BatchStates, simulate!
+export BatchLQR, DeviceLQR, BatchStates, simulate!
 
 # ------------------------------------------------------------------------------------------------ errors
 struct CcbError <: Exception
@@ -181,6 +181,45 @@ function BatchLQR(mechanism::Mechanism, bodyids, eqcids, Q, R, horizon; zd::Arra
     return BatchLQR(mh, Ku, zd, Matrix{Float64}(Fτd), eqcidx, N, kexit, iters)
 end
 
+"""
+    DeviceLQR(mechanism, bodyids, eqcids, Q, R, horizon; zd, Fτd)
+
+`BatchLQR` whose gain table never leaves the GPU (`ccb_lqr_create`): the right constructor when the gains are only used by
+`simulate!`.  `converged[s]` is `Ku[1] == Ku[2]` of lqr.jl:41 (meaningful for `horizon = Inf`).
+"""
+mutable struct DeviceLQR <: BatchController
+    mh::MechHandle
+    ptr::Ptr{Cvoid}
+    S::Int
+    kexit::Vector{Int32}; iters::Vector{Int32}; converged::Vector{Int32}
+end
+
+function DeviceLQR(mechanism::Mechanism, bodyids, eqcids, Q, R, horizon; zd::Array{Float64,3}, Fτd = zeros(length(eqcids), size(zd, 3)), device = 0)
+    Nb = length(mechanism.bodies)
+    @assert length(bodyids) == length(Q) == Nb "Missmatched length for bodies"                  # lqr.jl:59
+    @assert length(eqcids) == length(R) == size(Fτd, 1) "Missmatched length for constraints"    # lqr.jl:60
+    mh = MechHandle(mechanism)
+    Δt = mechanism.Δt
+    Qrm = permutedims(Matrix(cat(Q..., dims = (1, 2)) * Δt)); Rrm = permutedims(Matrix(cat(R..., dims = (1, 2)) * Δt))   # lqr.jl:18-19
+    inf = horizon / Δt == Inf
+    Ntemp = inf ? Integer(ceil(10 / Δt)) : Integer(ceil(horizon / Δt))                           # lqr.jl:21-27
+    eqcidx = Int32[findfirst(e -> getid(e) == id, collect(mechanism.eqconstraints)) - 1 for id in eqcids]
+    S = size(zd, 3); nu = length(eqcids)
+    kexit = zeros(Int32, S); iters = zeros(Int32, S); conv = zeros(Int32, S)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ccb_lqr_create, libccb), Cint,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int32, Int32,
+                 Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+                mh.ptr, device, S, zd, Fτd, eqcidx, nu, Qrm, 0, Rrm, 0, Ntemp, inf ? 1 : 0, C_NULL, out, kexit, iters, conv))
+    inf && any(==(0), conv) && @info "Riccati recursion did not converge."                       # lqr.jl:41
+    c = DeviceLQR(mh, out[], S, kexit, iters, conv)
+    finalizer(x -> ccall((:ccb_ctrl_destroy, libccb), Cint, (Ptr{Cvoid},), x.ptr), c)
+    return c
+end
+ctrl_handle(lqr::DeviceLQR, B, device) = lqr.ptr
+owns_handle(::DeviceLQR) = false
+owns_handle(::BatchController) = true
+
 function ctrl_handle(lqr::BatchLQR, B, device)
     n, nu, rows, S = size(lqr.K)
     d = Ref(CtrlDesc(lqr.N == Inf ? 2 : 3, nu, lqr.N == Inf ? 0 : Int32(lqr.N), B, pointer(lqr.eqcidx),
@@ -204,7 +243,7 @@ function simulate!(batch::BatchStates, Δt::Real, tend::Real, controller::Union{
     status = zeros(Int32, batch.B)
     rc = ccall((:ccb_simulate, libccb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}),
                batch.ptr, ch, 1, steps, C_NULL, record ? storage : C_NULL, status)
-    ch == C_NULL || ccall((:ccb_ctrl_destroy, libccb), Cint, (Ptr{Cvoid},), ch)
+    (ch == C_NULL || !owns_handle(controller)) || ccall((:ccb_ctrl_destroy, libccb), Cint, (Ptr{Cvoid},), ch)
     check(rc)
     return record ? storage : nothing
 end
