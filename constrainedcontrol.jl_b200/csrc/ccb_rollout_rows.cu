@@ -58,6 +58,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     constexpr int G = 5 * NJ, SPW = 32 / G;
     double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
     double* cst = smem + SPW * NJ * kGS;    // [NJ][kCS]
+    double* stash = cst + NJ * kCS;         // [SPW][NJ][16]: body residual d (6) and inverse rotational block Dinv (9) between evaluation and solve
     const int wl = threadIdx.x;
     const int sw = wl / G;
     const int q = wl - sw * G;
@@ -88,6 +89,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const double* gk_chi = gk + (swz * NJ + (has_c ? pos + 1 : pos)) * kGS;
     const double* cj = cst + pos * kCS;
     const double* ccj = cst + (has_c ? pos + 1 : pos) * kCS;
+    double* st_own = stash + (swz * NJ + pos) * 16;
 
     // ---- joint constants -> shared memory (one copy per joint position, shared by the systems of the warp)
     for (int i = wl; i < NJ * kCS; i += 32) {
@@ -106,7 +108,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const double pkdt = has_p ? dt / cst[(pos - 1) * kCS + 22] : 0.0;
 
     // ---- state in registers: the group's body (redundant in its 5 lanes) and my multiplier
-    double z[13], s[6], lam;
+    double z[13], lam;      // z[7..12]: (v1, w1) until the step's constants are formed, then the accepted Newton iterate (v2, w2)
     if (valid) {
 #pragma unroll
         for (int i = 0; i < 13; i++) z[i] = A.state[(size_t)sys * nst + 13 * b + i];
@@ -116,8 +118,6 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         for (int i = 0; i < 13; i++) z[i] = i == 3 ? 1.0 : 0.0;
         lam = 0.0;
     }
-#pragma unroll
-    for (int i = 0; i < 6; i++) s[i] = 0.0;
 
     // sum over the lanes of my system, evaluated in one fixed order so that every lane holds the same bits
     auto sys_sum = [&](double v) {
@@ -192,8 +192,6 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             const Q4 q2 = qmul(Q4{z[3], z[4], z[5], z[6]}, Q4{0.5 * dt * sq, 0.5 * dt * w.x, 0.5 * dt * w.y, 0.5 * dt * w.z});
             z[3] = q2.s; z[4] = q2.x; z[5] = q2.y; z[6] = q2.z;
         }
-#pragma unroll
-        for (int i = 0; i < 6; i++) s[i] = z[7 + i];
         // parent's knot pose (fixed for the step)
         V3 xa2 = {0.0, 0.0, 0.0};
         Q4 qa2 = {1.0, 0.0, 0.0, 0.0};
@@ -284,15 +282,8 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             __syncwarp();
         }
         // transposed copies for the force sums: lane r owns component r of G_own,B^T λ_own + G_child,A^T λ_child
-        double FB[5], FA[5];
-#pragma unroll
-        for (int t = 0; t < 5; t++) {
-            FB[t] = gk_own[12 * t + 6 + r];
-            FA[t] = has_c ? gk_chi[12 * t + r] : 0.0;
-        }
 
         // ---------------- newton! with lineSearch!
-        double p3[7], Dinv[9], Mw[9], d[6];
         double rowP[5], rowO[5], rowC[5], rhs;     // my row of S: parent block | own block | child block | rhs
         // G^T-type sum over the rows acting on my body: own joint (child side) + child joint (parent side)
         auto force_sum = [&](double mine, double* out6) {
@@ -300,7 +291,8 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
 #pragma unroll
             for (int t = 0; t < 5; t++) {
                 const double lo = shfl_d(mine, g0 + t), lc = shfl_d(mine, gc + t);
-                f = fma(FB[t], lo, fma(FA[t], lc, f));
+                f = fma(gk_own[12 * t + 6 + r], lo, f);                 // component r (lanes 0..4 of the group)
+                if (has_c) f = fma(gk_chi[12 * t + r], lc, f);
                 f5 = fma(gk_own[12 * t + 11], lo, f5);                 // sixth component: every lane, table read (broadcast)
                 if (has_c) f5 = fma(gk_chi[12 * t + 5], lc, f5);
             }
@@ -308,8 +300,13 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             for (int c = 0; c < 5; c++) out6[c] = shfl_d(f, g0 + c);
             out6[5] = f5;
         };
+        double dl = 0.0, ds[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // pending Newton step
+        double aeff = 0.0;                                        // line-search scale of the pending step (0: evaluate the accepted iterate)
         auto evaluate = [&](bool jac) -> double {
-            const V3 v2 = v3(s[0], s[1], s[2]), w2 = v3(s[3], s[4], s[5]);
+            const V3 v2 = v3(fma(-aeff, ds[0], z[7]), fma(-aeff, ds[1], z[8]), fma(-aeff, ds[2], z[9]));
+            const V3 w2 = v3(fma(-aeff, ds[3], z[10]), fma(-aeff, ds[4], z[11]), fma(-aeff, ds[5], z[12]));
+            const double lamt = fma(-aeff, dl, lam);
+            double p3[7], Dinv[9], Mw[9], d[6];
             const double sq2 = sqrt(c4 - dot(w2, w2));
             {
                 p3[0] = fma(dt, v2.x, z[0]); p3[1] = fma(dt, v2.y, z[1]); p3[2] = fma(dt, v2.z, z[2]);
@@ -322,7 +319,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             const V3 Jw2 = mat3_mul(J, w2);
             const V3 dR = sq2 * Jw2 + cross(w2, Jw2);
             double fs[6];
-            force_sum(lam, fs);
+            force_sum(lamt, fs);
             d[0] = fma(mass * idt, v2.x, c0[0]) - fs[0]; d[1] = fma(mass * idt, v2.y, c0[1]) - fs[1]; d[2] = fma(mass * idt, v2.z, c0[2]) - fs[2];
             d[3] = dR.x + c0[3] - fs[3]; d[4] = dR.y + c0[4] - fs[4]; d[5] = dR.z + c0[5] - fs[5];
             double ss = 0.0;
@@ -423,6 +420,12 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
                     if (rowpad) { rowO[t] = (t == r) ? 1.0 : 0.0; rowP[t] = 0.0; rowC[t] = 0.0; }
                 }
                 if (rowpad) rhs = 0.0;
+                // d and Dinv are needed again for the body step after the solve: park them in shared memory (3 words per lane)
+                if (lane_ok) {
+#pragma unroll
+                    for (int e = 0; e < 15; e++)
+                        if (e % 5 == r) st_own[e] = e < 6 ? d[e] : Dinv[e - 6];
+                }
             }
             return sqrt(sys_sum(ss));
         };
@@ -430,7 +433,8 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         // S dλ = rhs with one row per lane.  Elimination runs from the last row of the leaf joint to the first row of the
         // root joint, so a pivot row only has entries to its left (parent block + own block) and the rows it updates are the
         // earlier rows of its own block and the rows of the parent block: no fill.  On exit `rhs` holds dλ.
-        auto solve = [&](double& dl, double* ds) {
+        auto solve = [&](double& xdl, double* xds) {
+            __syncwarp();
             double myinv = 1.0;
 #pragma unroll
             for (int pp = NJ - 1; pp >= 0; pp--) {
@@ -475,13 +479,13 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
                     rhs = fma(-coef, xk, rhs);
                 }
             }
-            dl = rhs;
+            xdl = rhs;
             // body step ds = D^-1 (d + G_own,B^T dλ_own + G_child,A^T dλ_child)
             double fs[6];
-            force_sum(dl, fs);
-            const V3 dw = mat3_mul(Dinv, v3(d[3] + fs[3], d[4] + fs[4], d[5] + fs[5]));
-            ds[0] = kdt * (d[0] + fs[0]); ds[1] = kdt * (d[1] + fs[1]); ds[2] = kdt * (d[2] + fs[2]);
-            ds[3] = dw.x; ds[4] = dw.y; ds[5] = dw.z;
+            force_sum(xdl, fs);
+            const V3 dw = mat3_mul(st_own + 6, v3(st_own[3] + fs[3], st_own[4] + fs[4], st_own[5] + fs[5]));
+            xds[0] = kdt * (st_own[0] + fs[0]); xds[1] = kdt * (st_own[1] + fs[1]); xds[2] = kdt * (st_own[2] + fs[2]);
+            xds[3] = dw.x; xds[4] = dw.y; xds[5] = dw.z;
         };
 
         // newton! / lineSearch! as one loop around a single evaluation site.  The residual at an accepted line-search point is the
@@ -489,12 +493,9 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         // evaluation + one solve (instead of evaluation + solve + line-search evaluation), the iterates are unchanged.
         bool done = !valid, pending = false, first = true, out_of_iters = false;
         int n = 0, ls = 0;
-        double alpha = 1.0, full = 0.0, normf0 = 0.0, lam0 = lam;
-        double s0[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) s0[i] = s[i];
-        double dl = 0.0, ds[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double alpha = 1.0, full = 0.0, normf0 = 0.0;
         for (;;) {
+            aeff = pending ? alpha : 0.0;
             const double nfe = evaluate(true);
             bool want_solve = false;
             if (first) {
@@ -503,11 +504,11 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             } else if (pending) {
                 if (nfe >= normf0 && ls < A.line_iter) {          // lineSearch!: not decreased -> halve the step and try again
                     alpha *= 0.5; ls++;
-#pragma unroll
-                    for (int i = 0; i < 6; i++) s[i] = fma(-alpha, ds[i], s0[i]);
-                    lam = fma(-alpha, dl, lam0);
-                } else {                                          // accepted (or out of halvings)
+                } else {                                          // accepted (or out of halvings): s = s_prev - alpha * step
                     pending = false;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) z[7 + i] = fma(-alpha, ds[i], z[7 + i]);
+                    lam = fma(-alpha, dl, lam);
                     if (alpha * full < A.eps && nfe < A.eps) done = true;
                     normf0 = nfe;
                     if (!done && n >= A.newton_iter) { done = true; out_of_iters = true; }
@@ -530,16 +531,19 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             const double fullv = sqrt(sys_sum(sd));
             if (want_solve) {
                 n++;
-                full = fullv; dl = dl_new; lam0 = lam;
+                full = fullv; dl = dl_new;
 #pragma unroll
-                for (int i = 0; i < 6; i++) { ds[i] = ds_new[i]; s0[i] = s[i]; }
+                for (int i = 0; i < 6; i++) ds[i] = ds_new[i];
                 alpha = 1.0; ls = 0;
-#pragma unroll
-                for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
-                lam = lam0 - dl;
                 // a step below eps taken from a residual below eps ends the solve whatever scale the line search would pick
-                if (full < A.eps && normf0 < A.eps) done = true;
-                else pending = true;
+                if (full < A.eps && normf0 < A.eps) {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) z[7 + i] -= ds[i];
+                    lam -= dl;
+                    done = true;
+                } else {
+                    pending = true;
+                }
             }
             if (!__any_sync(0xffffffffu, pending)) break;
         }
@@ -549,15 +553,12 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             total_iters += it_used;
             if (!done) failed = true;
         }
-        if (!A.knot_input) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) z[7 + i] = s[i];      // updatestate!: (xc,qc,vc,wc) <- (x2,q2,v2,w2)
-        }
+        // updatestate!: (xc,qc,vc,wc) <- (x2,q2,v2,w2): z[0..6] already holds the knot, z[7..12] the converged (v2, w2)
     }
     if (valid && A.knot_input) {
         if (r == 0) {
 #pragma unroll
-            for (int i = 0; i < 6; i++) A.s_out[(size_t)sys * 6 * M.nb + 6 * b + i] = s[i];
+            for (int i = 0; i < 6; i++) A.s_out[(size_t)sys * 6 * M.nb + 6 * b + i] = z[7 + i];
         }
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     } else if (valid) {
@@ -578,7 +579,7 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cu
     for (int j = 0; j < 6; j++) ord.joint[j] = M.rows_order[j];
     const int G = 5 * M.nj, spw = 32 / G;
     const int grid = (a.B + spw - 1) / spw;
-    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS) * sizeof(double);
+    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 16) * sizeof(double);
     switch (M.nj) {
         case 1: rollout_rows_kernel<1><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
         case 2: rollout_rows_kernel<2><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
