@@ -249,12 +249,36 @@ class LQR(Controller):
     `LQR.from_gains` wraps gains that already exist (K [rows][nu][12 nb] or [S][rows][nu][12 nb])."""
 
     def __init__(self, mechanism: Mechanism, bodyids, eqcids, Q, R, horizon, xd=None, vd=None, qd=None, wd=None, Ftaud=None, device: int = 0,
-                 opts: Optional[dict] = None, Q_batch=None, R_batch=None):
+                 opts: Optional[dict] = None, Q_batch=None, R_batch=None, xtheta_d=None, vomega_d=None):
         """Q_batch [S][12 nb][12 nb] / R_batch [S][nu][nu] (optional): one assembled weight matrix per system instead of the
         shared block lists Q / R (a synthesis batch; they are scaled by Δt like lqr.jl:18-19)"""
         super().__init__()
         mech = mechanism
         nb = mech.nb
+        if Q_batch is None and Q is not None and len(Q) > 0 and all(np.ndim(q) == 0 for q in Q):
+            # minimal-coordinate constructor LQR(mechanism, controlledids, controlids, Q::Vector{T}, R::Vector{T}, horizon; xθd, vωd, Fτd)
+            # (lqr.jl:68-86): `bodyids` are the controlled eqcs (one 1-DoF joint per body), the setpoint is given in joint coordinates
+            controlledids, controlids = list(bodyids), list(eqcids)
+            xth = np.zeros(len(controlledids)) if xtheta_d is None else f64(xtheta_d).ravel()
+            vom = np.zeros(len(controlledids)) if vomega_d is None else f64(vomega_d).ravel()
+            Fta = np.zeros(len(controlids)) if Ftaud is None else f64(Ftaud).ravel()
+            if not (len(controlledids) == len(Q) == len(xth) == len(vom) == nb):          # lqr.jl:76
+                raise AssertionError("Missmatched length for bodies")
+            if not (len(controlids) == len(R) == len(Fta)):                               # lqr.jl:77
+                raise AssertionError("Missmatched length for constraints")
+            from .mechanism import propagate_minimal
+            saved = mech.state_vector().copy()
+            idx = [mech.eqc_index(i) for i in controlledids]
+            for e in idx:
+                if not mech.is_1dof(int(e)):
+                    raise AssertionError("Only 1 DOF joints are supported")
+            propagate_minimal(mech, {e: xth[k] for k, e in enumerate(idx)}, {e: vom[k] for k, e in enumerate(idx)})   # linearsystem(…6 args) lqr.jl:80
+            zdm = mech.state_vector().copy()
+            mech.set_state_vector(saved)
+            Q = [np.eye(12) * float(q) for q in Q]                                        # lqr.jl:82
+            R = [np.eye(1) * float(r) for r in R]                                         # lqr.jl:83
+            xd, qd, vd, wd = zdm[:, 0:3], zdm[:, 3:7], zdm[:, 7:10], zdm[:, 10:13]
+            bodyids, eqcids, Ftaud = [b.id for b in mech.bodies], controlids, Fta
         # lqr.jl:59-60
         if not (len(bodyids) == nb and (Q_batch is not None or len(Q) == nb)):
             raise AssertionError("Missmatched length for bodies")

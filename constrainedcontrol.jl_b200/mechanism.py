@@ -393,6 +393,58 @@ def setJointPosition(mech: Mechanism, eqc, coords):
         raise ValueError("setJointPosition needs a Revolute or Prismatic eqc")
 
 
+def setJointVelocity(mech: Mechanism, eqc, rate):
+    """velocity counterpart of setJointPosition: child (vc, wc) from the parent's velocities and the joint rate (θ' or d').
+    World angular velocity Ω = R(q) w (w is stored in the body frame):
+      Revolute   Ω_b = Ω_a + R_a ax θ' ;  v_b = v_a + Ω_a x (R_a p1) - Ω_b x (R_b p2)
+      Prismatic  Ω_b = Ω_a ;             v_b = v_a + Ω_a x (R_a (p1 + ax d)) + R_a ax d' - Ω_b x (R_b p2)"""
+    e = eqc if isinstance(eqc, EqualityConstraint) else geteqconstraint(mech, eqc)
+    assert len(e.constraints) == 1
+    j = e.constraints[0]
+    rate = float(np.atleast_1d(rate)[0])
+    a, b = j.parent, j.child
+    ax = j.axis / np.linalg.norm(j.axis)
+    if isinstance(a, Origin):
+        xa, qa, va, Wa = np.zeros(3), ONE_Q, np.zeros(3), np.zeros(3)
+    else:
+        xa, qa, va, Wa = a.state.xc, a.state.qc, a.state.vc, qrot(a.state.qc, a.state.wc)
+    xb, qb = b.state.xc, b.state.qc
+    r2 = qrot(qb, j.p2)
+    if j.nT == 3 and j.nR == 2:
+        Wb = Wa + qrot(qa, ax) * rate
+        vb = va + np.cross(Wa, qrot(qa, j.p1)) - np.cross(Wb, r2)
+    elif j.nT == 2 and j.nR == 3:
+        Wb = Wa
+        arm = xb + r2 - xa                       # = R_a (p1 + ax d)
+        vb = va + np.cross(Wa, arm) + qrot(qa, ax) * rate - np.cross(Wb, r2)
+    else:
+        raise ValueError("setJointVelocity needs a Revolute or Prismatic eqc")
+    b.state.vc = vb
+    b.state.wc = qrot(qconj(qb), Wb)
+
+
+def propagate_minimal(mech: Mechanism, coords: dict, rates: dict = None):
+    """forward kinematics of positions AND velocities over a tree of 1-DoF eqcs (eqc index -> coordinate / rate), root first:
+    the maximal-coordinate setpoint of the 6-argument `linearsystem` (reference src/control/lqr.jl:80)"""
+    rates = rates or {}
+    done = set()
+    pending = list(range(mech.ne))
+    guard = 0
+    while pending and guard < 10 * mech.ne + 10:
+        guard += 1
+        i = pending.pop(0)
+        e = mech.eqconstraints[i]
+        par = e.parent
+        if not isinstance(par, Origin) and id(par) not in done:
+            pending.append(i)
+            continue
+        setJointPosition(mech, e, [coords.get(i, 0.0)])
+        setJointVelocity(mech, e, [rates.get(i, 0.0)])
+        for j in e.constraints:
+            done.add(id(j.child))
+    return mech
+
+
 def propagate_positions(mech: Mechanism, coords: dict):
     """Forward kinematics over a tree: set every 1-DoF eqc named in `coords` (eqc index -> coordinate), root first."""
     done = set()

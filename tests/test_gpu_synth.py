@@ -129,3 +129,29 @@ def test_lqr_per_system_setpoints_device_resident(cc, orc):
     storage, final, status = cc.simulate(mech, 2.5, lqr, record=True, states=st0, return_status=True)
     assert np.all(status > 0)
     assert rel_err(storage.data, refs) < TOL
+
+
+def test_lqr_minimal_coordinate_ctor_prismatic_example(cc, orc):
+    # examples/lqr_prismatic.jl: LQR(mech, getid.(constraints), getid.(constraints), ones(1), ones(1), 10.) then simulate!(mech, 10., lqr)
+    mech, cfg = cc.examples.prismatic()
+    ids = cc.getid(mech.eqconstraints)
+    lqr = cc.LQR(mech, ids, ids, np.ones(1), np.ones(1), 10.0)        # setpoint: joint coordinate 0 -> link at the origin (lqr.jl:70-71,80)
+    assert np.allclose(lqr.zd[0, 0, 0:3], 0.0) and lqr.N == 1000
+    om = orc.OracleMech(mech.desc())
+    lin = om.linearize(lqr.zd[0], [0.0], [0])
+    ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], np.eye(12) * mech.dt, np.eye(1) * mech.dt, 1000)     # Q = I12 * 1, R = 1 (lqr.jl:82-83)
+    assert rel_err(lqr.K[0], ref["Ku"]) < TOL
+    st0 = mech.state_vector()[None].copy()                              # link displaced by 1 m along the joint axis
+    co = om.make_ctrl(1, kind="lqr_finite", eqc=[0], N=1000, K=ref["Ku"], zd=lqr.zd[0], Fd=np.zeros(1))
+    r = om.simulate(st0, 1000, ctrl=co, record=True)
+    storage = cc.simulate(mech, 10.0, lqr, record=True)
+    assert rel_err(storage.data, r["storage"]) < TOL
+    assert abs(mech.bodies[0].state.xc[0]) < 1e-2                       # regulated to the origin
+    # a non-zero joint setpoint on the cartpole: cart at y = 0.3, pole upright
+    mech2, cfg2 = cc.examples.cartpole()
+    ids2 = cc.getid(mech2.eqconstraints)
+    lqr2 = cc.LQR(mech2, ids2, [ids2[0]], np.ones(2), np.ones(1), 3.0, xtheta_d=[0.3, 0.0])
+    assert np.allclose(lqr2.zd[0, 0, 0:3], [0, 0.3, 0]) and np.allclose(lqr2.zd[0, 1, 0:3], [0, 0.3, 0.5])
+    lin2 = orc.OracleMech(mech2.desc()).linearize(lqr2.zd[0], [0.0], [0])
+    ref2 = orc.dlqr(lin2["A"], lin2["Bu"], lin2["Bl"], lin2["G"], np.eye(24) * mech2.dt, np.eye(1) * mech2.dt, 300)
+    assert rel_err(lqr2.K[0], ref2["Ku"]) < TOL
