@@ -23,8 +23,14 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 __host__ __device__ inline int dmma_ld(int n) { return (n % 16 == 4 || n % 16 == 12) ? n : n + 4; }
 
-template <int T>
-__global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int nu, int N, const double* __restrict__ At, const double* __restrict__ D,
+// NU1: scalar input (nu == 1): the nu x nu solve is a division and the generic elimination is compiled out (it costs ~128 registers).
+// STAGE (small time-invariant problems): Ã, Q and the previous P also live in shared memory, so an iteration touches global
+// memory only to store the gain row.
+#ifndef K4_MINB_NUM
+#define K4_MINB_NUM 24   // resident warps per SM the small-problem variants are compiled for (registers = 64 K / (32 * this))
+#endif
+template <int T, bool NU1, bool STAGE>
+__global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0 ? K4_MINB_NUM / T : 1) : 1) riccati_sweep_dmma_kernel(int n, int nu, int N, const double* __restrict__ At, const double* __restrict__ D,
                                                                      long long stride_t_A, long long stride_t_D, long long stride_s_A,
                                                                      long long stride_s_D, const double* __restrict__ Q, long long Q_bs,
                                                                      const double* __restrict__ R, long long R_bs, double* __restrict__ Ku,
@@ -41,7 +47,10 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
     double* Dp = RK + 8 * LD;                 // [n][8]   D padded to 8 columns
     double* Sc = Dp + (size_t)n * 8;          // [8][8]   R + D'P D
     double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
-    double* red = Rs + 64;                    // [T] partial sums
+    double* red = Rs + 64;                    // [T] partial sums (padded to 16)
+    double* Asm = red + 16;                   // STAGE: [n][LD] Ã
+    double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE: [n][LD] Q
+    double* Pold = Qsm + (STAGE ? (size_t)n * LD : 0);  // STAGE: [n][LD] previous P
     __shared__ int brk;
 
     const size_t s = blockIdx.x;
@@ -61,9 +70,14 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
     double* ps_c = Ps + (size_t)ra * LD + 2 * t4;             // my C elements of tile column j are at [8 j], [8 j + 1]
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
-    const double* q_c = Qs + (size_t)ra * n + 2 * t4;
+    const double* q_c = STAGE ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
+    double* po_c = STAGE ? Pold + (size_t)ra * LD + 2 * t4 : pg_c;      // where the previous P is kept for the ‖P - P+‖ test
 
     for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
+    if (STAGE) {
+        const double* A0 = At + s * stride_s_A;
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; Qsm[(size_t)i * LD + j] = Qs[e]; }
+    }
     for (int e = tid; e < 64; e += NT) { const int i = e >> 3, j = e & 7; Rs[e] = (i < nu && j < nu) ? Rg[i * nu + j] : (i == j ? 1.0 : 0.0); }
     for (int e = tid; e < 8 * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
     __syncthreads();
@@ -100,15 +114,16 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         {
             const int j0 = 8 * w, cb = min(j0 + g, n - 1);
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-            const double* ag = Ak + (size_t)t4 * n + cb;
+            const size_t lda = STAGE ? (size_t)LD : (size_t)n;
+            const double* ag = (STAGE ? Asm : Ak) + (size_t)t4 * lda + cb;
             const double* dr = DtP + g * LD + t4;
             int k0 = 0;
-            for (; k0 + 16 <= n; k0 += 16) {                              // four independent global loads in flight
-                const double b0 = __ldg(ag), b1 = __ldg(ag + 4 * (size_t)n), b2 = __ldg(ag + 8 * (size_t)n), b3 = __ldg(ag + 12 * (size_t)n);
+            for (; k0 + 16 <= n; k0 += 16) {                              // four independent loads in flight
+                const double b0 = ag[0], b1 = ag[4 * lda], b2 = ag[8 * lda], b3 = ag[12 * lda];
                 dmma(c0, c1, dr[k0], b0); dmma(e0, e1, dr[k0 + 4], b1); dmma(c0, c1, dr[k0 + 8], b2); dmma(e0, e1, dr[k0 + 12], b3);
-                ag += 16 * (size_t)n;
+                ag += 16 * lda;
             }
-            for (; k0 < n; k0 += 4) { dmma(c0, c1, dr[k0], __ldg(ag)); ag += 4 * (size_t)n; }
+            for (; k0 < n; k0 += 4) { dmma(c0, c1, dr[k0], ag[0]); ag += 4 * lda; }
             const int col = j0 + 2 * t4;
             if (col < n) Kk[g * LD + col] = c0 + e0;
             if (col + 1 < n) Kk[g * LD + col + 1] = c1 + e1;
@@ -120,7 +135,7 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         }
         __syncthreads();
         // ---- (C) Ku = Sc^-1 rhs
-        if (nu == 1) {                                                   // scalar input: Ku = rhs / Sc
+        if (NU1) {                                                       // scalar input: Ku = rhs / Sc
             const double inv = 1.0 / Sc[0], r00 = Rs[0];
             for (int c = tid; c < n; c += NT) {
                 const double x0 = Kk[c] * inv;
@@ -170,9 +185,9 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         // ---- (D) Abar = Ã - D Ku  (strip w; rank-8 update of Ã read from global in C layout)          lqr.jl:169
         double acc[T][2];
         {
-            const double* a_c = Ak + (size_t)ra * n + 2 * t4;
+            const double* a_c = STAGE ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
 #pragma unroll
-            for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? __ldg(a_c + 8 * j) : 0.0; acc[j][1] = ok1[j] ? __ldg(a_c + 8 * j + 1) : 0.0; }
+            for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? a_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? a_c[8 * j + 1] : 0.0; }
             const double a0 = -Dp[ra * 8 + t4], a1 = -Dp[ra * 8 + 4 + t4];
             const double *k0row = Kk + t4 * LD, *k1row = Kk + (4 + t4) * LD;
 #pragma unroll
@@ -200,13 +215,13 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < T; j++) {                                    // old P -> global copy (for the ‖P - P+‖ test), W -> shared
-            if (ok0[j]) { pg_c[8 * j] = ps_c[8 * j]; ps_c[8 * j] = acc[j][0]; }
-            if (ok1[j]) { pg_c[8 * j + 1] = ps_c[8 * j + 1]; ps_c[8 * j + 1] = acc[j][1]; }
+            if (ok0[j]) { po_c[8 * j] = ps_c[8 * j]; ps_c[8 * j] = acc[j][0]; }
+            if (ok1[j]) { po_c[8 * j + 1] = ps_c[8 * j + 1]; ps_c[8 * j + 1] = acc[j][1]; }
         }
         __syncthreads();
         // ---- (F) P+ = Q + Abar' W + Ku' (R Ku)  (strip w)                                              lqr.jl:170
 #pragma unroll
-        for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? __ldg(q_c + 8 * j) : 0.0; acc[j][1] = ok1[j] ? __ldg(q_c + 8 * j + 1) : 0.0; }
+        for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? q_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? q_c[8 * j + 1] : 0.0; }
         {
             const double* arow = As + (size_t)t4 * LD + ra;              // Abar^T fragment
             const double* brow = Ps + (size_t)t4 * LD;                   // W
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
         {
             double po[T][2];
 #pragma unroll
-            for (int j = 0; j < T; j++) { po[j][0] = ok0[j] ? pg_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? pg_c[8 * j + 1] : acc[j][1]; }
+            for (int j = 0; j < T; j++) { po[j][0] = ok0[j] ? po_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? po_c[8 * j + 1] : acc[j][1]; }
 #pragma unroll
             for (int j = 0; j < T; j++) { const double d0 = po[j][0] - acc[j][0], d1 = po[j][1] - acc[j][1]; nd = fma(d0, d0, nd); nd = fma(d1, d1, nd); }
         }
@@ -257,18 +272,18 @@ __global__ void __launch_bounds__(32 * T) riccati_sweep_dmma_kernel(int n, int n
     if (tid == 0) { kexit[s] = k; iters[s] = it; }
 }
 
-size_t dmma_smem_bytes(int n, int T) {
+size_t dmma_smem_bytes(int n, int T, bool stage) {
     const int LD = dmma_ld(n);
-    return ((size_t)2 * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + T + 8) * sizeof(double);
+    return ((size_t)(stage ? 5 : 2) * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
 }
 
-template <int T>
+template <int T, bool NU1, bool STAGE>
 int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D, long long stride_s_A,
                 long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku, int* kexit, int* iters, double* ws,
                 long long ws_stride, cudaStream_t stream) {
-    const size_t smem = dmma_smem_bytes(n, T);
-    CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    riccati_sweep_dmma_kernel<T><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
+    const size_t smem = dmma_smem_bytes(n, T, STAGE);
+    CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T, NU1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    riccati_sweep_dmma_kernel<T, NU1, STAGE><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
                                                              iters, ws, ws_stride);
     g_launches++;
     CCB_CUDA(cudaGetLastError());
@@ -281,20 +296,25 @@ int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, 
 bool riccati_dmma_eligible(int n, int nu) {
     if (n % 4 != 0 || nu > 8 || n < 8) return false;
     const int T = (n + 7) / 8;
-    return T <= 14 && dmma_smem_bytes(n, T) <= 227 * 1024;
+    return T <= 14 && dmma_smem_bytes(n, T, false) <= 227 * 1024;
 }
 
 int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                               long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                               int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
     const int T = (n + 7) / 8;
-#define CCB_DMMA_CASE(TT) \
-    case TT: return launch_dmma<TT>(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream);
+    const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
+#define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream
+#define CCB_DMMA_CASE(TT)                                                                      \
+    case TT:                                                                                   \
+        if constexpr (TT <= 5) { if (stage) return nu == 1 ? launch_dmma<TT, true, true>(CCB_DMMA_ARGS) : launch_dmma<TT, false, true>(CCB_DMMA_ARGS); } \
+        return nu == 1 ? launch_dmma<TT, true, false>(CCB_DMMA_ARGS) : launch_dmma<TT, false, false>(CCB_DMMA_ARGS);
     switch (T) {
         CCB_DMMA_CASE(1) CCB_DMMA_CASE(2) CCB_DMMA_CASE(3) CCB_DMMA_CASE(4) CCB_DMMA_CASE(5) CCB_DMMA_CASE(6) CCB_DMMA_CASE(7)
         CCB_DMMA_CASE(8) CCB_DMMA_CASE(9) CCB_DMMA_CASE(10) CCB_DMMA_CASE(11) CCB_DMMA_CASE(12) CCB_DMMA_CASE(13) CCB_DMMA_CASE(14)
     }
 #undef CCB_DMMA_CASE
+#undef CCB_DMMA_ARGS
     set_error("riccati_dmma: unsupported size");
     return CCB_E_UNSUPPORTED;
 }
