@@ -1,6 +1,7 @@
 // csrc/ccb_synth.cu -- C-ABI entry points for linearsystem / dlqr / LQR and TrackingLQR gain synthesis (K2 + K3).
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 #include "ccb_internal.h"
@@ -20,13 +21,45 @@ using namespace ccb;
 
 namespace {
 
-// tiny RAII pool of device allocations for one API call
+// Device scratch for one API call.  Small requests are carved from a per-device arena that persists across calls (cudaMalloc /
+// cudaFree synchronise the device and cost more than a cartpole synthesis batch); requests that do not fit (TrackingLQR batches:
+// tens of GB) fall back to cudaMalloc and are released when the call returns.  Not thread safe across calls on one device, like
+// the handles themselves.
+struct Arena { char* base = nullptr; size_t cap = 0, off = 0, want = 0; };
+static std::map<int, Arena> g_arenas;
+constexpr size_t kArenaMax = (size_t)4 << 30;
+
 struct Scratch {
     std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    Arena* ar = nullptr;
+    size_t start = 0, asked = 0;
+    Scratch() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) { ar = &g_arenas[dev]; start = ar->off; }
+    }
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+        if (!ar) return;
+        ar->off = start;
+        ar->want = std::max(ar->want, std::min(asked, kArenaMax));
+        if (start == 0 && ar->want > ar->cap) {      // grow for the next call
+            cudaFree(ar->base);
+            ar->base = nullptr; ar->cap = 0;
+            void* p = nullptr;
+            const size_t cap = ar->want + ar->want / 4;
+            if (cudaMalloc(&p, cap) == cudaSuccess) { ar->base = (char*)p; ar->cap = cap; } else cudaGetLastError();
+        }
+    }
     template <class T> int get(T** out, size_t count) {
+        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        asked += bytes;
+        if (ar && ar->base && ar->off + bytes <= ar->cap) {
+            *out = (T*)(ar->base + ar->off);
+            ar->off += bytes;
+            return CCB_OK;
+        }
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
         ptrs.push_back(p);
         *out = (T*)p;
