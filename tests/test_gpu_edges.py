@@ -1,0 +1,111 @@
+"""Edge cases of the C-ABI rollout / synthesis entry points on the GPU: empty and ragged batches, split rollouts (k0), error
+returns (the reference's @assert messages), per-system tables."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from helpers import cartpole_states, oracle_lqr_gains, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def cartpole_setup(cc, orc):
+    mech, cfg = cc.examples.cartpole()
+    o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=3.0)
+    lqr = cc.LQR.from_gains(mech, cfg["eqcids"], o["K"], o["N"], xd=cfg["xd"])
+    return mech, cfg, o, lqr
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 7])
+def test_ragged_batches_fill_partial_warps(cc, orc, cartpole_setup, B):
+    # K1r packs 3 cartpoles per warp: batches that leave lanes or whole system slots idle
+    mech, cfg, o, lqr = cartpole_setup
+    st0 = cartpole_states(cc, mech, 8, seed=9)[:B]
+    co = o["om"].make_ctrl(B, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
+    r = o["om"].simulate(st0, 120, ctrl=co, record=True)
+    sto, fin, status = cc.simulate(mech, 1.2, lqr, record=True, states=st0, return_status=True)
+    assert np.all(status > 0) and rel_err(sto.data, r["storage"]) < TOL and rel_err(fin, r["states"]) < TOL
+
+
+def test_zero_steps_and_split_rollout(cc, orc, cartpole_setup):
+    mech, cfg, o, lqr = cartpole_setup
+    B = 6
+    st0 = cartpole_states(cc, mech, B, seed=4)
+    batch = cc.Batch(mech, B)
+    batch.set_state(st0)
+    sto, status = batch.simulate(lqr, 1, 0, record=True)           # simulate!(mech, 0, ...): nothing happens
+    assert sto.shape[0] == 0 and np.array_equal(batch.get_state(), st0) and np.all(status == 0)
+    # one 200-step rollout == 120 steps followed by 80 steps with k0 = 121 (gain row K[k], lambda warm start and state carry over)
+    batch.simulate(lqr, 1, 200)
+    full = batch.get_state(want_lambda=True)
+    batch.set_state(st0)
+    batch.simulate(lqr, 1, 120)
+    batch.simulate(lqr, 121, 80)
+    split = batch.get_state(want_lambda=True)
+    assert np.array_equal(full[0], split[0]) and np.array_equal(full[1], split[1])
+
+
+def test_storage_semantics(cc, cartpole_setup):
+    # Storage records (xc,qc,vc,wc) at the START of each step: entry 0 is the initial state, the final state is not in it
+    mech, cfg, o, lqr = cartpole_setup
+    st0 = cartpole_states(cc, mech, 5, seed=6)
+    sto, fin, _ = cc.simulate(mech, 0.5, lqr, record=True, states=st0, return_status=True)
+    assert np.array_equal(sto.data[0], st0)
+    sto2, fin2, _ = cc.simulate(mech, 0.51, lqr, record=True, states=st0, return_status=True)     # ceil(tend / dt) = 51 steps
+    assert sto2.data.shape[0] == 51 and np.array_equal(sto2.data[50], fin)
+
+
+def test_per_system_gain_tables(cc, orc, cartpole_setup):
+    # K_bstride != 0: every system its own table (here: the shared table scaled per system) through ccb_ctrl_create
+    mech, cfg, o, lqr = cartpole_setup
+    B = 5
+    scale = np.linspace(0.8, 1.2, B)
+    Kb = o["K"][None] * scale[:, None, None, None]
+    st0 = cartpole_states(cc, mech, B, seed=8)
+    ctrl = cc.LQR.from_gains(mech, cfg["eqcids"], Kb, o["N"], xd=cfg["xd"])
+    sto, fin, status = cc.simulate(mech, 1.0, ctrl, record=True, states=st0, return_status=True)
+    for s in range(B):
+        co = o["om"].make_ctrl(1, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=Kb[s], zd=o["zd"], Fd=o["Fd"])
+        r = o["om"].simulate(st0[s:s + 1], 100, ctrl=co, record=True)
+        assert rel_err(sto.data[:, s], r["storage"][:, 0]) < TOL, s
+
+
+def test_error_returns(cc, cartpole_setup):
+    mech, cfg, o, lqr = cartpole_setup
+    L = cc._lib.lib()
+    # kernel selection that does not apply to the mechanism
+    sw, cfg_s = cc.examples.sawyer(__file__.replace("test_gpu_edges.py", "golden/sawyer_arm.json"))
+    with pytest.raises(cc.CcbError, match="row-per-lane"):
+        cc.simulate(sw, 0.02, None, states=sw.batch_states(2), lanes=5)
+    mech_d, _ = cc.examples.deltabot()
+    with pytest.raises(cc.CcbError, match="serial chain"):
+        cc.simulate(mech_d, 0.02, None, states=mech_d.batch_states(2), lanes=6)
+    with pytest.raises(cc.CcbError, match="lanes per system"):
+        cc.simulate(mech, 0.02, None, states=mech.batch_states(2), lanes=3)
+    # controller laid out for another batch size
+    Kb = np.repeat(o["K"][None], 4, axis=0)
+    ctrl4 = cc.LQR.from_gains(mech, cfg["eqcids"], Kb, o["N"], xd=cfg["xd"])
+    with pytest.raises(cc.CcbError):
+        cc.simulate(mech, 0.02, ctrl4, states=mech.batch_states(6))
+    # the reference's assertion messages
+    with pytest.raises(AssertionError, match="Missmatched length for bodies"):
+        cc.LQR(mech, cc.getid(mech.bodies)[:1], cfg["eqcids"], cfg["Q"], cfg["R"], 1.0)
+    with pytest.raises(AssertionError, match="Missmatched length for constraints"):
+        cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"] + cfg["R"], 1.0)
+    # NULL / bad arguments straight at the ABI: error code + message, never a crash
+    assert L.ccb_simulate(None, None, C.c_int32(1), C.c_int32(1), None, None, None) == -1
+    assert b"NULL" in L.ccb_last_error() or b"bad" in L.ccb_last_error()
+    assert L.ccb_dlqr(C.c_int32(0), C.c_int32(0), C.c_int32(4), C.c_int32(1), C.c_int32(0), C.c_int32(5), None, None, None, None, None, C.c_int64(0), None,
+                      C.c_int64(0), None, None, None) == -1
+    # more controlled inputs than the Riccati kernels support
+    n, nu = 12, 9
+    A = np.eye(n)[None]; Bu = np.ones((1, n, nu)); Q = np.eye(n); R = np.eye(nu)
+    with pytest.raises(cc.CcbError, match="8 controlled"):
+        cc.dlqr(A, Bu, np.zeros((1, n, 0)), np.zeros((1, 0, n)), Q, R, 5)
+    # no such device
+    with pytest.raises(cc.CcbError, match="CUDA device"):
+        cc.lqr_synthesize(mech, o["zd"][None], np.zeros((1, 1)), [0], np.eye(24), np.eye(1), 5, device=99)

@@ -1,7 +1,7 @@
 """Parity (small) + throughput (full size) sweep over the BASELINE configs C1..C5; writes JSON lines to stdout.
 Not the bench: a measurement helper whose output is archived under profiles/."""
 import json, math, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np

@@ -1,7 +1,7 @@
 """2+ GPU check of the one collective of the path: all-gather of gain tables synthesised on different ranks.
 torchrun --nproc-per-node N tools_nccl_check.py"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, torch, torch.distributed as dist
 import ccb200 as cc

@@ -1,6 +1,7 @@
 """small, short invocation of the rollout kernel for ncu (one launch, 4096 systems x 100 steps)"""
-import sys, math
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle'); sys.path.insert(0, '/root/repo/tests')
+import sys, math, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/oracle'); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc, orc
 from helpers import oracle_lqr_gains, cartpole_states
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100

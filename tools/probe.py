@@ -1,6 +1,6 @@
 """quick timing probe of the headline rollout config (not the bench): python tools_probe.py "B,steps,lanes[,spw];..." """
 import sys, time, math, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/oracle'); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc, orc
 from helpers import oracle_lqr_gains, cartpole_states

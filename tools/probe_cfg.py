@@ -1,6 +1,6 @@
 """rollout timing probe for a named config: python tools_probe_cfg.py sawyer|npend8|npend32 B steps "lanes,lanes,..." """
 import sys, os, time, math
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc
 from helpers import zd_of

@@ -1,6 +1,6 @@
 """device-time probe of the synthesis kernels: python tools_synth_probe.py "name,S[,N];..." ; CCB_NO_DMMA=1 selects K3"""
 import sys, os, math, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc
 from helpers import zd_of

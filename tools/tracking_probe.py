@@ -1,6 +1,6 @@
 """C4 at scale: 64 Sawyer reference trajectories x N steps -> TrackingLQR synthesis -> 16 perturbed rollouts each"""
 import sys, os, time, math
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
 import numpy as np, ccb200 as cc
 NT = int(sys.argv[1]) if len(sys.argv) > 1 else 64
