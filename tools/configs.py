@@ -125,11 +125,38 @@ if want("C5b"):
     goals = np.stack([g1.ravel(), g2.ravel()], axis=1)
     B = goals.shape[0]
     st0 = mech.batch_states(B)
-    pid = cc.PID(mech, cfg["eqcids"], goals, P=cfg["P"], I=cfg["I"], D=cfg["D"])
     batch = cc.Batch(mech, B)
     def go():
+        pid = cc.PID(mech, cfg["eqcids"], goals, P=cfg["P"], I=cfg["I"], D=cfg["D"])   # fresh controller: integratederrors persist otherwise (pid.jl:76)
         batch.set_state(st0)
         return batch.simulate(pid, 1, 1000)
     t, (_, status) = timed(go)
     print(json.dumps(dict(config="C5 pid_doublependulum 32x32 goal sweep", B=B, steps=1000, rollout_s=t, sim_steps_per_s=B * 1000 / t,
                           newton_per_step=float(np.abs(status).mean() / 1000), flagged=int((status <= 0).sum()))), flush=True)
+
+def run_uncontrolled(tag, n, B, steps):
+    """hanging n-pendulum swinging freely: the tree solve at scale without the (ill-conditioned) upright LQR"""
+    mech, cfg = cc.examples.cartpole_n_pendulum(n)
+    rng = np.random.default_rng(3)
+    st = np.zeros((B, mech.nb, 13))
+    for s_ in range(B):
+        ph = rng.uniform(-0.05, 0.05, size=n); ph[0] += math.pi
+        cc.examples.set_cartpole_pose(mech, rng.uniform(-0.5, 0.5), ph); st[s_] = mech.state_vector()
+    om = orc.OracleMech(mech.desc())
+    r = om.simulate(st[:4], 40, record=True, nthreads=4)
+    sto, fin, status = cc.simulate(mech, 0.4, None, record=True, states=st[:4], return_status=True)
+    batch = cc.Batch(mech, B)
+    def go():
+        batch.set_state(st)
+        return batch.simulate(None, 1, steps)
+    t, (_, status) = timed(go)
+    t0 = time.time(); om.simulate(st[:16], 50, nthreads=8); tc = time.time() - t0
+    print(json.dumps(dict(config=tag, nb=mech.nb, ml=mech.ml, B=B, steps=steps, rollout_s=t, sim_steps_per_s=B * steps / t,
+                          newton_per_step=float(np.abs(status).mean() / steps), failed=int((status <= 0).sum()),
+                          rollout_rel_err=rel_err(sto.data, r["storage"]), cpu_sim_steps_per_s_8thr=16 * 50 / tc)), flush=True)
+
+
+if want("C3c"):
+    run_uncontrolled("C3 n_pendulum n=8 hanging chain, uncontrolled", 8, 1024, 1000)
+if want("C3d"):
+    run_uncontrolled("C3 n_pendulum n=32 hanging chain, uncontrolled", 32, 1024, 200)
