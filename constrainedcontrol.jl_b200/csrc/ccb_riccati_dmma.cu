@@ -24,12 +24,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 __host__ __device__ inline int dmma_ld(int n) { return (n % 16 == 4 || n % 16 == 12) ? n : n + 4; }
 
 // NU1: scalar input (nu == 1): the nu x nu solve is a division and the generic elimination is compiled out (it costs ~128 registers).
-// STAGE (small time-invariant problems): Ã, Q and the previous P also live in shared memory, so an iteration touches global
-// memory only to store the gain row.
+// STAGE (time-invariant problems): 2 = Ã, Q and the previous P also live in shared memory, so an iteration touches global memory only
+// to store the gain row (small n); 1 = only Ã is staged (n <= 84: three n x n matrices fit in 227 KB); 0 = everything streams from L2.
 #ifndef K4_MINB_NUM
 #define K4_MINB_NUM 24   // resident warps per SM the small-problem variants are compiled for (registers = 64 K / (32 * this))
 #endif
-template <int T, bool NU1, bool STAGE>
+template <int T, bool NU1, int STAGE>
 __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0 ? K4_MINB_NUM / T : 1) : 1) riccati_sweep_dmma_kernel(int n, int nu, int N, const double* __restrict__ At, const double* __restrict__ D,
                                                                      long long stride_t_A, long long stride_t_D, long long stride_s_A,
                                                                      long long stride_s_D, const double* __restrict__ Q, long long Q_bs,
@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
     double* red = Rs + 64;                    // [T] partial sums (padded to 16)
     double* Asm = red + 16;                   // STAGE: [n][LD] Ã
-    double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE: [n][LD] Q
-    double* Pold = Qsm + (STAGE ? (size_t)n * LD : 0);  // STAGE: [n][LD] previous P
+    double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE == 2: [n][LD] Q
+    double* Pold = Qsm + (STAGE == 2 ? (size_t)n * LD : 0);  // STAGE == 2: [n][LD] previous P
     __shared__ int brk;
 
     const size_t s = blockIdx.x;
@@ -70,13 +70,13 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* ps_c = Ps + (size_t)ra * LD + 2 * t4;             // my C elements of tile column j are at [8 j], [8 j + 1]
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
-    const double* q_c = STAGE ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
-    double* po_c = STAGE ? Pold + (size_t)ra * LD + 2 * t4 : pg_c;      // where the previous P is kept for the ‖P - P+‖ test
+    const double* q_c = STAGE == 2 ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
+    double* po_c = STAGE == 2 ? Pold + (size_t)ra * LD + 2 * t4 : pg_c;      // where the previous P is kept for the ‖P - P+‖ test
 
     for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
     if (STAGE) {
         const double* A0 = At + s * stride_s_A;
-        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; Qsm[(size_t)i * LD + j] = Qs[e]; }
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (STAGE == 2) Qsm[(size_t)i * LD + j] = Qs[e]; }
     }
     for (int e = tid; e < 64; e += NT) { const int i = e >> 3, j = e & 7; Rs[e] = (i < nu && j < nu) ? Rg[i * nu + j] : (i == j ? 1.0 : 0.0); }
     for (int e = tid; e < 8 * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
@@ -272,12 +272,12 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     if (tid == 0) { kexit[s] = k; iters[s] = it; }
 }
 
-size_t dmma_smem_bytes(int n, int T, bool stage) {
+size_t dmma_smem_bytes(int n, int T, int stage) {
     const int LD = dmma_ld(n);
-    return ((size_t)(stage ? 5 : 2) * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
+    return ((size_t)(stage == 2 ? 5 : stage == 1 ? 3 : 2) * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
 }
 
-template <int T, bool NU1, bool STAGE>
+template <int T, bool NU1, int STAGE>
 int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D, long long stride_s_A,
                 long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku, int* kexit, int* iters, double* ws,
                 long long ws_stride, cudaStream_t stream) {
@@ -296,7 +296,7 @@ int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, 
 bool riccati_dmma_eligible(int n, int nu) {
     if (n % 4 != 0 || nu > 8 || n < 8) return false;
     const int T = (n + 7) / 8;
-    return T <= 14 && dmma_smem_bytes(n, T, false) <= 227 * 1024;
+    return T <= 14 && dmma_smem_bytes(n, T, 0) <= 227 * 1024;
 }
 
 int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
@@ -304,11 +304,13 @@ int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, con
                               int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
     const int T = (n + 7) / 8;
     const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
+    const bool stage_a = stride_t_A == 0 && !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;   // 72 <= n <= 84: Ã only (+2 %; for smaller n the extra shared memory costs more residency than it saves)
 #define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream
 #define CCB_DMMA_CASE(TT)                                                                      \
     case TT:                                                                                   \
-        if constexpr (TT <= 5) { if (stage) return nu == 1 ? launch_dmma<TT, true, true>(CCB_DMMA_ARGS) : launch_dmma<TT, false, true>(CCB_DMMA_ARGS); } \
-        return nu == 1 ? launch_dmma<TT, true, false>(CCB_DMMA_ARGS) : launch_dmma<TT, false, false>(CCB_DMMA_ARGS);
+        if constexpr (TT <= 5) { if (stage) return nu == 1 ? launch_dmma<TT, true, 2>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 2>(CCB_DMMA_ARGS); } \
+        if constexpr (TT >= 9 && TT <= 11) { if (stage_a) return nu == 1 ? launch_dmma<TT, true, 1>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 1>(CCB_DMMA_ARGS); } \
+        return nu == 1 ? launch_dmma<TT, true, 0>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 0>(CCB_DMMA_ARGS);
     switch (T) {
         CCB_DMMA_CASE(1) CCB_DMMA_CASE(2) CCB_DMMA_CASE(3) CCB_DMMA_CASE(4) CCB_DMMA_CASE(5) CCB_DMMA_CASE(6) CCB_DMMA_CASE(7)
         CCB_DMMA_CASE(8) CCB_DMMA_CASE(9) CCB_DMMA_CASE(10) CCB_DMMA_CASE(11) CCB_DMMA_CASE(12) CCB_DMMA_CASE(13) CCB_DMMA_CASE(14)
