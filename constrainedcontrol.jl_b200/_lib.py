@@ -56,7 +56,7 @@ SYMBOLS = [
 def build(verbose: bool = False) -> str:
     """compile csrc/*.cu for sm_100a into csrc/libccb.so (nvcc cross-compiles without a GPU)"""
     out = None if verbose else subprocess.DEVNULL
-    subprocess.check_call(["make", "-C", CSRC, "libccb.so"], stdout=out)
+    subprocess.check_call(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC, "libccb.so"], stdout=out)
     return SO_PATH
 
 
