@@ -37,6 +37,12 @@ __device__ __forceinline__ void cta_gemm_t(int M, int N, int K, const double* __
             double a[TM], b[TN];
 #pragma unroll
             for (int i = 0; i < TM; i++) a[i] = (i0 + i < M) ? (TA ? A[(size_t)k * lda + i0 + i] : A[(size_t)(i0 + i) * lda + k]) : 0.0;
+            // the left operands of the projection (G, Bλ) are block sparse with exact zeros (a row of G touches 2 of the nb bodies):
+            // skipping a zero multiplicand skips the loads of B as well and adds exactly nothing
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < TM; i++) any |= (a[i] != 0.0);
+            if (!any) continue;
 #pragma unroll
             for (int j = 0; j < TN; j++) b[j] = (j0 + j < N) ? B[(size_t)k * ldb + j0 + j] : 0.0;
 #pragma unroll
@@ -86,12 +92,19 @@ __device__ void cta_lu_solve(int m, double* Mx, int ldm, double* Bx, int ldb, in
         }
         __syncthreads();
         const double inv = 1.0 / Mx[(size_t)k * ldm + k];
-        const int rows = m - k - 1, wid = (m - k - 1) + nr;   // columns k+1..m-1 of M and all of B
-        for (int t = tid; t < rows * wid; t += RT) {
-            const int i = k + 1 + t / wid, jj = t % wid;
-            const double l = Mx[(size_t)i * ldm + k] * inv;
-            if (jj < m - k - 1) Mx[(size_t)i * ldm + k + 1 + jj] = fma(-l, Mx[(size_t)k * ldm + k + 1 + jj], Mx[(size_t)i * ldm + k + 1 + jj]);
-            else Bx[(size_t)i * ldb + (jj - (m - k - 1))] = fma(-l, Bx[(size_t)k * ldb + (jj - (m - k - 1))], Bx[(size_t)i * ldb + (jj - (m - k - 1))]);
+        // elimination: a thread owns one column of [M | B] (no integer divisions in the loop), RT / 128 row groups
+        const int wid = (m - k - 1) + nr;
+        const int jj0 = tid & 127, ig = tid >> 7, ng = RT >> 7;
+        for (int jj = jj0; jj < wid; jj += 128) {
+            double* col;
+            size_t ld;
+            if (jj < m - k - 1) { col = Mx + k + 1 + jj; ld = ldm; }
+            else { col = Bx + (jj - (m - k - 1)); ld = ldb; }
+            const double pk = col[(size_t)k * ld];
+            for (int i = k + 1 + ig; i < m; i += ng) {
+                const double l = Mx[(size_t)i * ldm + k] * inv;
+                col[(size_t)i * ld] = fma(-l, pk, col[(size_t)i * ld]);
+            }
         }
         __syncthreads();
     }
@@ -110,7 +123,7 @@ __device__ void cta_lu_solve(int m, double* Mx, int ldm, double* Bx, int ldb, in
 // workspace per problem: GB [ml][ml], Y [ml][n+nu]
 __global__ void __launch_bounds__(RT) riccati_project_kernel(int n, int nu, int ml, const double* __restrict__ A, const double* __restrict__ Bu,
                                                              const double* __restrict__ Bl, const double* __restrict__ G, double* __restrict__ At,
-                                                             double* __restrict__ D, double* __restrict__ ws) {
+                                                             double* __restrict__ D, double* __restrict__ ws, int use_smem) {
     __shared__ int piv;
     __shared__ double red[32];
     const size_t p = blockIdx.x;
@@ -120,7 +133,10 @@ __global__ void __launch_bounds__(RT) riccati_project_kernel(int n, int nu, int 
         for (int t = threadIdx.x; t < n * nu; t += RT) D[t] = Bu[t];
         return;
     }
-    double* GB = ws + p * ((size_t)ml * ml + (size_t)ml * (n + nu));
+    // G Bλ and its right-hand sides live in shared memory when they fit (the pivoted LU is a chain of ml barriers: at global-memory
+    // latency it dominated the whole projection), else in the global workspace (32-pendulum: ml = 165)
+    extern __shared__ double proj_sm[];
+    double* GB = use_smem ? proj_sm : ws + p * ((size_t)ml * ml + (size_t)ml * (n + nu));
     double* Y = GB + (size_t)ml * ml;
     cta_gemm<false>(ml, ml, n, G, n, Bl, ml, GB, ml, nullptr, 0, 1.0);
     cta_gemm<false>(ml, n, n, G, n, A, n, Y, n + nu, nullptr, 0, 1.0);
@@ -252,7 +268,10 @@ size_t riccati_sweep_ws_doubles(int n, int nu) { return 4 * (size_t)n * n + 2 * 
 
 int riccati_project_device(int P, int n, int nu, int ml, const double* A, const double* Bu, const double* Bl, const double* G, double* At, double* D,
                            double* ws, cudaStream_t stream) {
-    riccati_project_kernel<<<P, RT, 0, stream>>>(n, nu, ml, A, Bu, Bl, G, At, D, ws);
+    const size_t smem = ((size_t)ml * ml + (size_t)ml * (n + nu)) * sizeof(double);
+    const int use_smem = smem <= 200 * 1024 ? 1 : 0;
+    if (use_smem) CCB_CUDA(cudaFuncSetAttribute(riccati_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    riccati_project_kernel<<<P, RT, use_smem ? smem : 0, stream>>>(n, nu, ml, A, Bu, Bl, G, At, D, ws, use_smem);
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;
