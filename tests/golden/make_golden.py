@@ -16,3 +16,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import ccb200 as cc
 desc = cc.urdf.parse_urdf("/root/reference/examples/examples_files/sawyer_arm.urdf")
 json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_arm.json"), "w"), indent=1)
+
+# the branching Sawyer description with fixed joints (reference examples/examples_files/sawyer_simple.urdf): SURVEY 8(f) n3
+desc = cc.urdf.parse_urdf("/root/reference/examples/examples_files/sawyer_simple.urdf")
+json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_simple.json"), "w"), indent=1)

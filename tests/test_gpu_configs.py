@@ -253,3 +253,37 @@ def test_c2_full_size_properties(cc, orc):
     co = o["om"].make_ctrl(16, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
     r = o["om"].simulate(st0[:16], steps, ctrl=co, nthreads=8)
     assert rel_err(fin[:16], r["states"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ branching URDF tree with fixed joints
+def test_sawyer_simple_urdf_branching_tree_with_fixed_joints(cc, orc):
+    # examples/examples_files/sawyer_simple.urdf: pedestal + arm base welded to the origin (6-row Fixed joints), head and arm branch at right_l0
+    mech = cc.urdf.mechanism_from_json(os.path.join(GOLD, "sawyer_simple.json"), floating=False, g=-9.81, dt=0.01)
+    assert (mech.nb, mech.ne, mech.ml) == (10, 10, 52)
+    g = cc.handle(mech).graph()
+    om = orc.OracleMech(mech.desc())
+    go = om.graph()
+    for k in go:
+        assert np.array_equal(g[k], go[k]), k
+    assert len(g["loop_edges"]) == 0
+    # the arm falls under gravity from the zero configuration (uncontrolled): general kernel K1 (not a single chain, 6-row joints)
+    B = 6
+    st0 = mech.batch_states(B)
+    rng = np.random.default_rng(1)
+    st0[:, :, 10:13] += 0.05 * rng.normal(size=(B, mech.nb, 3)) * 0          # (velocities must satisfy the joints: keep the rest state)
+    r = om.simulate(st0, 80, record=True, nthreads=6)
+    sto, fin, status = cc.simulate(mech, 0.8, None, record=True, states=st0, return_status=True)
+    assert np.all(status > 0) and np.all(r["iters"] > 0)
+    assert rel_err(sto.data, r["storage"]) < TOL
+    assert constraint_violation(cc, mech, fin[:2]) < 1e-9
+    assert np.abs(fin[0, 0, 0:3] - st0[0, 0, 0:3]).max() < 1e-12            # the welded pedestal does not move
+    # PID on the first arm joint (right_j0) while everything else swings
+    j0 = mech.eqconstraints[2]
+    pid = cc.PID(mech, [j0.id], [0.3], P=[40.0], I=[0.0], D=[8.0])
+    eqc = [mech.eqc_index(j0.id)]
+    integ = np.zeros((B, 1)); last = np.zeros((B, 1))
+    co = om.make_ctrl(B, kind="pid", eqc=eqc, P=[40.0], I=[0.0], D=[8.0], goal=np.full((B, 1), 0.3), pid_int=integ, pid_last=last)
+    r2 = om.simulate(st0, 60, ctrl=co, record=True, nthreads=6)
+    sto2, fin2, status2 = cc.simulate(mech, 0.6, pid, record=True, states=st0, return_status=True)
+    assert np.all(status2 > 0)
+    assert rel_err(sto2.data, r2["storage"]) < 1e-8
