@@ -470,45 +470,50 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
             ds[3] = dw.x; ds[4] = dw.y; ds[5] = dw.z;
         };
 
-        bool done = false;
-        double normf0 = 0.0;
-        int it_used = 0;
-        for (int n = 1; n <= A.newton_iter; n++) {
-            if (done) break;
-            const double nf = evaluate(true);
-            if (n == 1) normf0 = nf;
+        // newton! / lineSearch! around a single evaluation site (as in K1r): the evaluation at an accepted line-search point is the
+        // evaluation the next Newton iteration starts from, so it also forms the Jacobian rows; the iterates are unchanged
+        bool done = false, first = true;
+        double normf0 = 0.0, alpha = 1.0, full = 0.0, lam0 = lam;
+        double s0[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) s0[i] = s[i];
+        int n = 0, ls = 0;
+        for (;;) {
+            const double nfe = evaluate(true);
+            if (first) {
+                normf0 = nfe;
+                first = false;
+            } else {
+                if (nfe >= normf0 && ls < A.line_iter) {          // lineSearch!: not decreased -> halve the step and try again
+                    alpha *= 0.5; ls++;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) s[i] = fma(-alpha, ds[i], s0[i]);
+                    lam = fma(-alpha, dl, lam0);
+                    continue;
+                }
+                if (alpha * full < A.eps && nfe < A.eps) done = true;
+                normf0 = nfe;
+                if (done || n >= A.newton_iter) break;
+            }
             solve();
+            n++;
             double sd = lane_ok ? dl * dl : 0.0;
             if (lane_ok && r == 0) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) sd = fma(ds[i], ds[i], sd);
             }
-            const double full = sqrt(sys_sum(sd));
-            double s0[6];
+            full = sqrt(sys_sum(sd));
 #pragma unroll
             for (int i = 0; i < 6; i++) s0[i] = s[i];
-            const double lam0 = lam;
-            const bool tiny = full < A.eps && normf0 < A.eps;
-            double alpha = 1.0, normf1 = normf0;
-            if (tiny) {
+            lam0 = lam;
+            alpha = 1.0; ls = 0;
 #pragma unroll
-                for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
-                lam = lam0 - dl;
-            } else {
-                for (int ls = 0; ls <= A.line_iter; ls++) {
-#pragma unroll
-                    for (int i = 0; i < 6; i++) s[i] = fma(-alpha, ds[i], s0[i]);
-                    lam = fma(-alpha, dl, lam0);
-                    normf1 = evaluate(false);
-                    if (normf1 >= normf0 && ls < A.line_iter) alpha *= 0.5;
-                    else break;
-                }
-            }
-            it_used = n;
-            const double nd = alpha * full;
-            if (tiny || (nd < A.eps && normf1 < A.eps)) done = true;
-            normf0 = normf1;
+            for (int i = 0; i < 6; i++) s[i] = s0[i] - ds[i];
+            lam = lam0 - dl;
+            // a step below eps taken from a residual below eps ends the solve whatever scale the line search would pick
+            if (full < A.eps && normf0 < A.eps) { done = true; break; }
         }
+        const int it_used = n;
         total_iters += it_used;
         if (!done) failed = true;
         if (!A.knot_input) {
