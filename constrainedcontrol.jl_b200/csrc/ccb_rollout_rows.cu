@@ -58,7 +58,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     constexpr int G = 5 * NJ, SPW = 32 / G;
     double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
     double* cst = smem + SPW * NJ * kGS;    // [NJ][kCS]
-    double* stash = cst + NJ * kCS;         // [SPW][NJ][16]: body residual d (6) and inverse rotational block Dinv (9) between evaluation and solve
+    double* stash = cst + NJ * kCS;         // [SPW][NJ][17]: body residual d (6) and inverse rotational block Dinv (9) between evaluation and solve
     const int wl = threadIdx.x;
     const int sw = wl / G;
     const int q = wl - sw * G;
@@ -89,7 +89,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const double* gk_chi = gk + (swz * NJ + (has_c ? pos + 1 : pos)) * kGS;
     const double* cj = cst + pos * kCS;
     const double* ccj = cst + (has_c ? pos + 1 : pos) * kCS;
-    double* st_own = stash + (swz * NJ + pos) * 16;
+    double* st_own = stash + (swz * NJ + pos) * 17;     // stride 17: the groups of a warp land in distinct banks
 
     // ---- joint constants -> shared memory (one copy per joint position, shared by the systems of the warp)
     for (int i = wl; i < NJ * kCS; i += 32) {
@@ -579,7 +579,7 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cu
     for (int j = 0; j < 6; j++) ord.joint[j] = M.rows_order[j];
     const int G = 5 * M.nj, spw = 32 / G;
     const int grid = (a.B + spw - 1) / spw;
-    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 16) * sizeof(double);
+    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
     switch (M.nj) {
         case 1: rollout_rows_kernel<1><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
         case 2: rollout_rows_kernel<2><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
