@@ -26,7 +26,8 @@ namespace ccb {
 
 namespace {
 
-constexpr int kGS = 62;   // doubles per joint group in the knot-row table: 5 rows x 12 (+2: groups land in distinct banks)
+constexpr int kGS = 70;   // doubles per joint group in the knot-row table: 5 rows x 12, padded so that (a) the double2 row loads of the 6 groups of a
+                          // warp hit distinct 16-byte bank groups (35 g mod 8) and (b) the 5-lane column reads of the force sums barely overlap (6 g mod 16)
 constexpr int kCS = 24;   // doubles of constants per joint: p1 3, p2 3, qoff 4, axis 3, J 9, mass 1 (+1)
 
 struct RowsOrder { int joint[6]; };
