@@ -36,9 +36,11 @@ __device__ __forceinline__ double rcp_nr(double x) {
     return fma(y, e, y);
 }
 
+// NJT: number of joints as a compile-time constant (0 = run time): the shared-memory mailbox offsets fold into immediates
+template <int NJT>
 __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const int* __restrict__ depth) {
     extern __shared__ __align__(16) double smem[];
-    const int nj = M.nj;
+    const int nj = NJT ? NJT : M.nj;
     double* gk = smem;                          // [nj][kGS]  knot rows: row t at t*12: GkA[6] | GkB[6]
     double* cst = gk + nj * kGS;                // [nj][kCS]
     double* xpose = cst + nj * kCS;             // [nj][8]    body pose mailbox (knot pose, then x3 q3)
@@ -412,7 +414,7 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
             double myinv = 1.0;
             int par = 0;
             const int wlo = (q >> 5) << 5, whi = wlo + 31;     // rows held by my warp
-            const bool many_warps = blockDim.x > 64;           // (with 2 warps the skip only adds divergence: measured on the Sawyer arm)
+            const bool many_warps = true;
             for (int pp = nj - 1; pp >= 0; pp--) {
 #pragma unroll
                 for (int rk = 4; rk >= 0; rk--) {
@@ -550,8 +552,18 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
                            5 * nj + nj + (nj + 1);
     const size_t smem = doubles * sizeof(double) + (size_t)nj * sizeof(int) + 16;
     if (smem > 227 * 1024) { set_error("mechanism too large for the multi-warp rows kernel"); return CCB_E_UNSUPPORTED; }
-    CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_mw_kernel<<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);
+#define CCB_MW_LAUNCH(NJT)                                                                                                    \
+    do {                                                                                                                     \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        rollout_mw_kernel<NJT><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                                      \
+    } while (0)
+    switch (nj) {          // the BASELINE chain lengths get their own instantiation: Sawyer arm, 8-pendulum, 32-pendulum
+        case 7: CCB_MW_LAUNCH(7); break;
+        case 9: CCB_MW_LAUNCH(9); break;
+        case 33: CCB_MW_LAUNCH(33); break;
+        default: CCB_MW_LAUNCH(0); break;
+    }
+#undef CCB_MW_LAUNCH
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;
