@@ -12,7 +12,7 @@ using LinearAlgebra
 
 const libccb = get(ENV, "CCB_LIB", joinpath(@__DIR__, "..", "csrc", "libccb.so"))
 
-export BatchLQR, DeviceLQR, BatchStates, simulate!
+export BatchLQR, DeviceLQR, DeviceTrackingLQR, BatchPID, BatchStates, replicate!, simulate!
 
 # ------------------------------------------------------------------------------------------------ errors
 struct CcbError <: Exception
@@ -219,6 +219,77 @@ end
 ctrl_handle(lqr::DeviceLQR, B, device) = lqr.ptr
 owns_handle(::DeviceLQR) = false
 owns_handle(::BatchController) = true
+
+"""
+    DeviceTrackingLQR(mechanism, storage::Array{Float64,4}, Fτ::Array{Float64,3}, eqcids, Q, R)
+
+`TrackingLQR(mechanism, storage, Fτ, eqcids, Q, R)` (reference src/control/lqr_tracking.jl:17-43) for S reference trajectories at once:
+`storage[:, i, k, s]` = (x, q, v, ω) of body i at step k of trajectory s (the transpose `storage.x[i][k] -> xd[k][i]` of
+lqr_tracking.jl:30-37 is the memory layout itself), `Fτ[:, k, s]` the feed-forward inputs.  Gains, desired trajectory and feed-forward
+stay on the GPU (`ccb_tracking_create`); `replicate!(ctrl, per)` lets `per` consecutive systems of a batch share one trajectory.
+"""
+mutable struct DeviceTrackingLQR <: BatchController
+    mh::MechHandle
+    ptr::Ptr{Cvoid}
+    S::Int; N::Int
+    kexit::Vector{Int32}; iters::Vector{Int32}
+end
+
+function DeviceTrackingLQR(mechanism::Mechanism, storage::Array{Float64,4}, Fτ::Array{Float64,3}, eqcids, Q, R; device = 0)
+    Nb = length(mechanism.bodies)
+    @assert size(storage, 1) == 13 && size(storage, 2) == Nb
+    N, S = size(storage, 3), size(storage, 4)
+    mh = MechHandle(mechanism)
+    Δt = mechanism.Δt
+    Qrm = permutedims(Matrix(cat(Q..., dims = (1, 2)) * Δt)); Rrm = permutedims(Matrix(cat(R..., dims = (1, 2)) * Δt))   # lqr_tracking.jl:22-23
+    eqcidx = Int32[findfirst(e -> getid(e) == id, collect(mechanism.eqconstraints)) - 1 for id in eqcids]
+    nu = length(eqcids)
+    @assert size(Fτ) == (nu, N, S)
+    kexit = zeros(Int32, S); iters = zeros(Int32, S)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ccb_tracking_create, libccb), Cint,
+                (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}},
+                 Ptr{Int32}, Ptr{Int32}),
+                mh.ptr, device, S, N, storage, Fτ, eqcidx, nu, Qrm, Rrm, C_NULL, out, kexit, iters))
+    c = DeviceTrackingLQR(mh, out[], S, N, kexit, iters)
+    finalizer(x -> ccall((:ccb_ctrl_destroy, libccb), Cint, (Ptr{Cvoid},), x.ptr), c)
+    return c
+end
+replicate!(c::Union{DeviceLQR,DeviceTrackingLQR}, per::Integer) = (check(ccall((:ccb_ctrl_set_replication, libccb), Cint, (Ptr{Cvoid}, Int32), c.ptr, per)); c)
+ctrl_handle(c::DeviceTrackingLQR, B, device) = c.ptr
+owns_handle(::DeviceTrackingLQR) = false
+
+"""
+    BatchPID(mechanism, eqcids, goals::Matrix; P, I, D)
+
+`PID(mechanism, eqcids, goals; P, I, D)` (reference src/control/pid.jl:25-39) with one goal column per system; the controller memory
+(`integratederrors`, `lasterrors`, pid.jl:9-10) lives on the device and persists across `simulate!` calls like pid.jl:76.
+"""
+mutable struct BatchPID <: BatchController
+    mh::MechHandle
+    ptr::Ptr{Cvoid}
+    B::Int
+end
+
+function BatchPID(mechanism::Mechanism, eqcids, goals::Matrix{Float64}; P = zeros(length(eqcids)), I = zeros(length(eqcids)), D = zeros(length(eqcids)), device = 0)
+    mh = MechHandle(mechanism)
+    nu = length(eqcids); B = size(goals, 2)
+    @assert size(goals, 1) == nu
+    eqcidx = Int32[findfirst(e -> getid(e) == id, collect(mechanism.eqconstraints)) - 1 for id in eqcids]
+    Pv, Iv, Dv = Float64.(P), Float64.(I), Float64.(D)
+    d = Ref(CtrlDesc(5, nu, 0, B, pointer(eqcidx), C_NULL, 0, C_NULL, 0, C_NULL, 0, C_NULL, 0, pointer(Pv), pointer(Iv), pointer(Dv), pointer(goals), B == 1 ? 0 : nu))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve eqcidx Pv Iv Dv goals begin
+        rc = ccall((:ccb_ctrl_create, libccb), Cint, (Ptr{Cvoid}, Ref{CtrlDesc}, Int32, Ref{Ptr{Cvoid}}), mh.ptr, d, device, out)
+    end
+    rc == 0 || (rc == -1 && throw(AssertionError("Only 1 DOF joints are supported")))      # pid.jl:20,36
+    check(rc)
+    c = BatchPID(mh, out[], B)
+    finalizer(x -> ccall((:ccb_ctrl_destroy, libccb), Cint, (Ptr{Cvoid},), x.ptr), c)
+    return c
+end
+ctrl_handle(c::BatchPID, B, device) = c.ptr
+owns_handle(::BatchPID) = false
 
 function ctrl_handle(lqr::BatchLQR, B, device)
     n, nu, rows, S = size(lqr.K)
