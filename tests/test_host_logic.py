@@ -1,0 +1,70 @@
+"""Host-side logic that needs no device: config dimensions, Storage views, weight assembly, batch sharding."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_config_dimensions_match_survey_appendix_b(cc):
+    # config -> (Nb, Ne, m_lambda, n = 12 Nb, mu)
+    table = {
+        "pendulum": (1, 1, 5, 12, 1), "cartpole": (2, 2, 10, 24, 1), "triple_cartpole": (4, 4, 20, 48, 1), "deltabot": (5, 5, 33, 60, 2),
+        "doublependulum": (2, 2, 10, 24, 2), "acrobot": (2, 2, 10, 24, 1), "prismatic": (1, 1, 5, 12, 1),
+    }
+    for name, (nb, ne, ml, n, mu) in table.items():
+        mech, cfg = getattr(cc.examples, name)()
+        assert (mech.nb, mech.ne, mech.ml, 12 * mech.nb, len(cfg["eqcids"])) == (nb, ne, ml, n, mu), name
+        assert np.abs(mech.constraint_values()).max() < 1e-12, name           # every example starts on its constraint manifold
+    for n_links, dims in ((8, (9, 9, 45, 108, 1)), (32, (33, 33, 165, 396, 1))):
+        mech, cfg = cc.examples.cartpole_n_pendulum(n_links)
+        assert (mech.nb, mech.ne, mech.ml, 12 * mech.nb, len(cfg["eqcids"])) == dims
+    mech, cfg = cc.examples.sawyer(os.path.join(GOLD, "sawyer_arm.json"))
+    assert (mech.nb, mech.ne, mech.ml, 12 * mech.nb, len(cfg["eqcids"])) == (7, 7, 35, 84, 7)
+    # deltabot: one eqc with three joints (Revolute + Revolute + FixedOrientation = 13 rows), examples/lqr_deltabot.jl:25
+    mech, _ = cc.examples.deltabot()
+    assert sorted(len(e) for e in mech.eqconstraints) == [5, 5, 5, 5, 13]
+
+
+def test_ids_eqcs_first_and_lookup(cc):
+    mech, cfg = cc.examples.cartpole()
+    assert cc.getid(mech.eqconstraints) == [1, 2] and cc.getid(mech.bodies) == [3, 4]      # eqcs 1..Ne, bodies Ne+1..Ne+Nb (SURVEY A.1 decision)
+    assert mech.eqc_index(cfg["eqcids"][0]) == 0 and mech.body_index(4) == 1
+    assert cc.geteqconstraint(mech, "joint2").id == 2
+    assert mech.is_1dof(0) and mech.is_1dof(1)
+    d, _ = cc.examples.deltabot()
+    assert [d.is_1dof(i) for i in range(5)] == [True, True, False, True, True]
+
+
+def test_storage_views_are_body_major(cc):
+    st = cc.Storage(4, 2, B=3)
+    st.data[...] = np.arange(st.data.size).reshape(st.data.shape)
+    assert len(st) == 4 and len(st.x) == 2
+    assert np.array_equal(st.x[1][2], st.data[2, 0, 1, 0:3]) and np.array_equal(st.q[0][3], st.data[3, 0, 0, 3:7])
+    assert np.array_equal(st.v[1][0], st.data[0, 0, 1, 7:10]) and np.array_equal(st.w[0][1], st.data[1, 0, 0, 10:13])
+
+
+def test_blockdiag_is_cat_dims_1_2(cc):
+    Q = cc.blockdiag([np.eye(2) * 2, np.ones((1, 1)) * 5])
+    assert Q.shape == (3, 3) and np.array_equal(Q, np.array([[2, 0, 0], [0, 2, 0], [0, 0, 5.0]]))
+
+
+@pytest.mark.parametrize("total,world", [(4096, 8), (1024, 8), (10, 3), (7, 8), (1, 1)])
+def test_shard_ranges_partition_the_batch(cc, total, world):
+    r = [cc.dist.shard_range(total, k, world) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][1] == total
+    assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+    sizes = [hi - lo for lo, hi in r]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_pid_constructor_scalar_form_and_asserts(cc):
+    # pid.jl:16-23: PID(mechanism, eqcid::Integer, goal; P, I, D) wraps the scalars
+    mech, cfg = cc.examples.pendulum()
+    pid = cc.PID(mech, cfg["eqcids"][0], math.pi / 2, P=10.0, I=1.0, D=2.0)
+    assert pid.goals.shape == (1, 1) and pid.P.tolist() == [10.0]
+    d, _ = cc.examples.deltabot()
+    with pytest.raises(AssertionError, match="Only 1 DOF"):
+        cc.PID(d, d.eqconstraints[2].id, 0.0)
