@@ -287,3 +287,36 @@ def test_sawyer_simple_urdf_branching_tree_with_fixed_joints(cc, orc):
     sto2, fin2, status2 = cc.simulate(mech, 0.6, pid, record=True, states=st0, return_status=True)
     assert np.all(status2 > 0)
     assert rel_err(sto2.data, r2["storage"]) < 1e-8
+
+
+def test_c4_sawyer_pid_and_infinite_horizon_lqr_on_the_long_chain_kernel(cc, orc):
+    # the control laws not covered above on K1m (7-joint chain): PID (pid.jl:69-88) and LQR with horizon = Inf (lqr.jl:116-139)
+    mech, cfg = cc.examples.sawyer(os.path.join(GOLD, "sawyer_arm.json"))
+    om = orc.OracleMech(mech.desc())
+    B = 5
+    st0 = sawyer_states(cc, mech, B, 7, 0.02)
+    ids = [mech.eqconstraints[1].id, mech.eqconstraints[4].id]
+    eqc = [mech.eqc_index(i) for i in ids]
+    goals = np.stack([np.linspace(-0.2, 0.2, B), np.linspace(0.1, -0.1, B)], axis=1)
+    P, I, D = [8.0, 1.0], [0.5, 0.1], [1.0, 0.05]
+    integ = np.zeros((B, 2)); last = np.zeros((B, 2))
+    co = om.make_ctrl(B, kind="pid", eqc=eqc, P=P, I=I, D=D, goal=goals, pid_int=integ, pid_last=last)
+    r = om.simulate(st0, 80, ctrl=co, record=True, nthreads=5)
+    assert np.all(r["iters"] > 0)
+    for lanes in (0, 1):
+        pid = cc.PID(mech, ids, goals, P=P, I=I, D=D)
+        sto, fin, status = cc.simulate(mech, 0.8, pid, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        assert rel_err(sto.data, r["storage"]) < 1e-8, lanes
+        gi, gl = pid.pid_state(B)
+        assert rel_err(gi, integ) < 1e-8 and rel_err(gl, last) < 1e-8
+    # horizon = Inf: Ntemp = ceil(10/dt) Riccati steps, only Ku[1] kept and applied at every k (lqr.jl:26,42,134)
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], math.inf, xd=cfg["xd"], qd=cfg["qd"])
+    assert lqr.K.shape == (1, 1, 7, 84)
+    zd = zd_of(mech, cfg)
+    eqc_all = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    st1 = sawyer_states(cc, mech, B, 8, 0.005)
+    co = om.make_ctrl(B, kind="lqr_inf", eqc=eqc_all, K=lqr.K[0], zd=zd, Fd=np.zeros(7))
+    r = om.simulate(st1, 100, ctrl=co, record=True, nthreads=5)
+    sto, fin, status = cc.simulate(mech, 1.0, lqr, record=True, states=st1, return_status=True)
+    assert np.all(status > 0) and rel_err(sto.data, r["storage"]) < TOL
