@@ -97,43 +97,76 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             for (int e = tid; e < n * 8; e += NT) { const int i = e >> 3, j = e & 7; Dp[e] = j < nu ? Dk[(size_t)i * nu + j] : 0.0; }
             __syncthreads();
         }
-        // ---- (A) D'P: tile column w.  a = D^T fragment, b = P fragment
-        {
-            const int j0 = 8 * w, cb = min(j0 + g, n - 1);
-            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-            for (int k0 = 0; k0 < n; k0 += 8) {
-                dmma(c0, c1, Dp[(k0 + t4) * 8 + g], Ps[(size_t)(k0 + t4) * LD + cb]);
-                if (k0 + 4 < n) dmma(e0, e1, Dp[(k0 + 4 + t4) * 8 + g], Ps[(size_t)(k0 + 4 + t4) * LD + cb]);
+        if (NU1) {
+            // scalar input: D'P, D'P Ã and R + D'P D are vector-matrix products -- plain FMAs (a padded 8-row DMMA tile would do 8x the work)
+            for (int j = tid; j < n; j += NT) {                       // (A) DtP[j] = sum_k D[k] P[k][j]
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double* pc = Ps + j;
+                for (int k0 = 0; k0 < n; k0 += 4) {
+                    a0 = fma(Dp[8 * k0], pc[(size_t)k0 * LD], a0); a1 = fma(Dp[8 * (k0 + 1)], pc[(size_t)(k0 + 1) * LD], a1);
+                    a2 = fma(Dp[8 * (k0 + 2)], pc[(size_t)(k0 + 2) * LD], a2); a3 = fma(Dp[8 * (k0 + 3)], pc[(size_t)(k0 + 3) * LD], a3);
+                }
+                DtP[j] = (a0 + a1) + (a2 + a3);
             }
-            const int col = j0 + 2 * t4;
-            if (col < n) DtP[g * LD + col] = c0 + e0;
-            if (col + 1 < n) DtP[g * LD + col + 1] = c1 + e1;
-        }
-        __syncthreads();
-        // ---- (B) rhs = D'P Ã (tile column w; Ã from global) and Sc = R + D'P D (warp 0)
-        {
-            const int j0 = 8 * w, cb = min(j0 + g, n - 1);
-            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            __syncthreads();
             const size_t lda = STAGE ? (size_t)LD : (size_t)n;
-            const double* ag = (STAGE ? Asm : Ak) + (size_t)t4 * lda + cb;
-            const double* dr = DtP + g * LD + t4;
-            int k0 = 0;
-            for (; k0 + 16 <= n; k0 += 16) {                              // four independent loads in flight
-                const double b0 = ag[0], b1 = ag[4 * lda], b2 = ag[8 * lda], b3 = ag[12 * lda];
-                dmma(c0, c1, dr[k0], b0); dmma(e0, e1, dr[k0 + 4], b1); dmma(c0, c1, dr[k0 + 8], b2); dmma(e0, e1, dr[k0 + 12], b3);
-                ag += 16 * lda;
+            const double* Ab = STAGE ? Asm : Ak;
+            for (int j = tid; j < n; j += NT) {                       // (B) rhs[j] = sum_k DtP[k] Ã[k][j]
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double* ac = Ab + j;
+                for (int k0 = 0; k0 < n; k0 += 4) {
+                    a0 = fma(DtP[k0], ac[(size_t)k0 * lda], a0); a1 = fma(DtP[k0 + 1], ac[(size_t)(k0 + 1) * lda], a1);
+                    a2 = fma(DtP[k0 + 2], ac[(size_t)(k0 + 2) * lda], a2); a3 = fma(DtP[k0 + 3], ac[(size_t)(k0 + 3) * lda], a3);
+                }
+                Kk[j] = (a0 + a1) + (a2 + a3);
             }
-            for (; k0 < n; k0 += 4) { dmma(c0, c1, dr[k0], ag[0]); ag += 4 * lda; }
-            const int col = j0 + 2 * t4;
-            if (col < n) Kk[g * LD + col] = c0 + e0;
-            if (col + 1 < n) Kk[g * LD + col + 1] = c1 + e1;
-            if (w == 0) {
-                double s0 = Rs[g * 8 + 2 * t4], s1 = Rs[g * 8 + 2 * t4 + 1];
-                for (int k0 = 0; k0 < n; k0 += 4) dmma(s0, s1, DtP[g * LD + k0 + t4], Dp[(k0 + t4) * 8 + g]);
-                Sc[g * 8 + 2 * t4] = s0; Sc[g * 8 + 2 * t4 + 1] = s1;
+            if (w == 0) {                                             // Sc = R + sum_k DtP[k] D[k]  (one warp, fixed-order reduction)
+                double a0 = 0.0;
+                for (int k0 = lane; k0 < n; k0 += 32) a0 = fma(DtP[k0], Dp[8 * k0], a0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                if (lane == 0) Sc[0] = Rs[0] + a0;
             }
+            __syncthreads();
+        } else {
+        // ---- (A) D'P: tile column w.  a = D^T fragment, b = P fragment
+            {
+                const int j0 = 8 * w, cb = min(j0 + g, n - 1);
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                for (int k0 = 0; k0 < n; k0 += 8) {
+                    dmma(c0, c1, Dp[(k0 + t4) * 8 + g], Ps[(size_t)(k0 + t4) * LD + cb]);
+                    if (k0 + 4 < n) dmma(e0, e1, Dp[(k0 + 4 + t4) * 8 + g], Ps[(size_t)(k0 + 4 + t4) * LD + cb]);
+                }
+                const int col = j0 + 2 * t4;
+                if (col < n) DtP[g * LD + col] = c0 + e0;
+                if (col + 1 < n) DtP[g * LD + col + 1] = c1 + e1;
+            }
+            __syncthreads();
+            // ---- (B) rhs = D'P Ã (tile column w; Ã from global) and Sc = R + D'P D (warp 0)
+            {
+                const int j0 = 8 * w, cb = min(j0 + g, n - 1);
+                double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                const size_t lda = STAGE ? (size_t)LD : (size_t)n;
+                const double* ag = (STAGE ? Asm : Ak) + (size_t)t4 * lda + cb;
+                const double* dr = DtP + g * LD + t4;
+                int k0 = 0;
+                for (; k0 + 16 <= n; k0 += 16) {                              // four independent loads in flight
+                    const double b0 = ag[0], b1 = ag[4 * lda], b2 = ag[8 * lda], b3 = ag[12 * lda];
+                    dmma(c0, c1, dr[k0], b0); dmma(e0, e1, dr[k0 + 4], b1); dmma(c0, c1, dr[k0 + 8], b2); dmma(e0, e1, dr[k0 + 12], b3);
+                    ag += 16 * lda;
+                }
+                for (; k0 < n; k0 += 4) { dmma(c0, c1, dr[k0], ag[0]); ag += 4 * lda; }
+                const int col = j0 + 2 * t4;
+                if (col < n) Kk[g * LD + col] = c0 + e0;
+                if (col + 1 < n) Kk[g * LD + col + 1] = c1 + e1;
+                if (w == 0) {
+                    double s0 = Rs[g * 8 + 2 * t4], s1 = Rs[g * 8 + 2 * t4 + 1];
+                    for (int k0 = 0; k0 < n; k0 += 4) dmma(s0, s1, DtP[g * LD + k0 + t4], Dp[(k0 + t4) * 8 + g]);
+                    Sc[g * 8 + 2 * t4] = s0; Sc[g * 8 + 2 * t4 + 1] = s1;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- (C) Ku = Sc^-1 rhs
         if (NU1) {                                                       // scalar input: Ku = rhs / Sc
             const double inv = 1.0 / Sc[0], r00 = Rs[0];
@@ -188,14 +221,24 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             const double* a_c = STAGE ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
 #pragma unroll
             for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? a_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? a_c[8 * j + 1] : 0.0; }
-            const double a0 = -Dp[ra * 8 + t4], a1 = -Dp[ra * 8 + 4 + t4];
-            const double *k0row = Kk + t4 * LD, *k1row = Kk + (4 + t4) * LD;
+            if (NU1) {
+                const double dneg = -Dp[ra * 8];
+                const double* kc = Kk + 2 * t4;
 #pragma unroll
-            for (int j = 0; j < T; j++) {
-                dmma(acc[j][0], acc[j][1], a0, k0row[cbj[j]]);
-                dmma(acc[j][0], acc[j][1], a1, k1row[cbj[j]]);
-                if (ok0[j]) as_c[8 * j] = acc[j][0];
-                if (ok1[j]) as_c[8 * j + 1] = acc[j][1];
+                for (int j = 0; j < T; j++) {
+                    if (ok0[j]) as_c[8 * j] = fma(dneg, kc[8 * j], acc[j][0]);
+                    if (ok1[j]) as_c[8 * j + 1] = fma(dneg, kc[8 * j + 1], acc[j][1]);
+                }
+            } else {
+                const double a0 = -Dp[ra * 8 + t4], a1 = -Dp[ra * 8 + 4 + t4];
+                const double *k0row = Kk + t4 * LD, *k1row = Kk + (4 + t4) * LD;
+#pragma unroll
+                for (int j = 0; j < T; j++) {
+                    dmma(acc[j][0], acc[j][1], a0, k0row[cbj[j]]);
+                    dmma(acc[j][0], acc[j][1], a1, k1row[cbj[j]]);
+                    if (ok0[j]) as_c[8 * j] = acc[j][0];
+                    if (ok1[j]) as_c[8 * j + 1] = acc[j][1];
+                }
             }
         }
         __syncthreads();
@@ -232,12 +275,22 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 arow += 4 * LD; brow += 4 * LD;
             }
         }
+        if (NU1) {                                                       // + Ku' (R Ku): rank one
+            const double ki = Kk[ra];
+            const double* rc = RK + 2 * t4;
 #pragma unroll
-        for (int k0 = 0; k0 < 8; k0 += 4) {
-            const double a = Kk[(k0 + t4) * LD + ra];                    // Ku^T fragment
-            const double* brow = RK + (k0 + t4) * LD;
+            for (int j = 0; j < T; j++) {
+                if (ok0[j]) acc[j][0] = fma(ki, rc[8 * j], acc[j][0]);
+                if (ok1[j]) acc[j][1] = fma(ki, rc[8 * j + 1], acc[j][1]);
+            }
+        } else {
 #pragma unroll
-            for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const double a = Kk[(k0 + t4) * LD + ra];                // Ku^T fragment
+                const double* brow = RK + (k0 + t4) * LD;
+#pragma unroll
+                for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+            }
         }
         double nd = 0.0;                                                 // ‖P - P+‖_F^2 over my fragments (old P from the global copy)
         {
