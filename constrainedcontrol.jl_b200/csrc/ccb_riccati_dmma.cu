@@ -41,16 +41,17 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     const int LD = dmma_ld(n);
     double* Ps = sm;                          // [n][LD]  P, then W = P Abar
     double* As = Ps + (size_t)n * LD;         // [n][LD]  Abar
-    double* DtP = As + (size_t)n * LD;        // [8][LD]  D'P
-    double* Kk = DtP + 8 * LD;                // [8][LD]  rhs, then Ku (rows >= nu are zero)
-    double* RK = Kk + 8 * LD;                 // [8][LD]  R Ku
-    double* Dp = RK + 8 * LD;                 // [n][8]   D padded to 8 columns
+    constexpr int NR = NU1 ? 1 : 8;           // rows of the skinny operands (nu padded to one 8-row tile unless the input is scalar)
+    double* DtP = As + (size_t)n * LD;        // [NR][LD]  D'P
+    double* Kk = DtP + NR * LD;               // [NR][LD]  rhs, then Ku (rows >= nu are zero)
+    double* RK = Kk + NR * LD;                // [NR][LD]  R Ku
+    double* Dp = RK + NR * LD;                // [n][8]   D padded to 8 columns
     double* Sc = Dp + (size_t)n * 8;          // [8][8]   R + D'P D
     double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
     double* red = Rs + 64;                    // [T] partial sums (padded to 16)
     double* Asm = red + 16;                   // STAGE: [n][LD] Ã
     double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE == 2: [n][LD] Q
-    double* Pold = Qsm + (STAGE == 2 ? (size_t)n * LD : 0);  // STAGE == 2: [n][LD] previous P
+    double* Pold = Qsm + (STAGE == 2 ? (size_t)n * LD : 0);  // (unused since the previous P of a staged problem is kept in registers)
     __shared__ int brk;
 
     const size_t s = blockIdx.x;
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
     const double* q_c = STAGE == 2 ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
-    double* po_c = STAGE == 2 ? Pold + (size_t)ra * LD + 2 * t4 : pg_c;      // where the previous P is kept for the ‖P - P+‖ test
+    double* po_c = pg_c;                                      // STAGE < 2: the previous P is kept in the global copy for the ‖P - P+‖ test
+    (void)Pold;
 
     for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
     if (STAGE) {
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (STAGE == 2) Qsm[(size_t)i * LD + j] = Qs[e]; }
     }
     for (int e = tid; e < 64; e += NT) { const int i = e >> 3, j = e & 7; Rs[e] = (i < nu && j < nu) ? Rg[i * nu + j] : (i == j ? 1.0 : 0.0); }
-    for (int e = tid; e < 8 * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
+    for (int e = tid; e < NR * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
     __syncthreads();
 
     int k, it = 0;
@@ -256,10 +258,17 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             }
         }
         __syncthreads();
+        double pold[STAGE == 2 ? T : 1][2];
 #pragma unroll
-        for (int j = 0; j < T; j++) {                                    // old P -> global copy (for the ‖P - P+‖ test), W -> shared
-            if (ok0[j]) { po_c[8 * j] = ps_c[8 * j]; ps_c[8 * j] = acc[j][0]; }
-            if (ok1[j]) { po_c[8 * j + 1] = ps_c[8 * j + 1]; ps_c[8 * j + 1] = acc[j][1]; }
+        for (int j = 0; j < T; j++) {                                    // old P -> registers / global copy (for the ‖P - P+‖ test), W -> shared
+            if constexpr (STAGE == 2) {                                  // small staged problems: previous P stays in registers
+                pold[j][0] = ps_c[8 * j]; pold[j][1] = ps_c[8 * j + 1];
+                if (ok0[j]) ps_c[8 * j] = acc[j][0];
+                if (ok1[j]) ps_c[8 * j + 1] = acc[j][1];
+            } else {
+                if (ok0[j]) { po_c[8 * j] = ps_c[8 * j]; ps_c[8 * j] = acc[j][0]; }
+                if (ok1[j]) { po_c[8 * j + 1] = ps_c[8 * j + 1]; ps_c[8 * j + 1] = acc[j][1]; }
+            }
         }
         __syncthreads();
         // ---- (F) P+ = Q + Abar' W + Ku' (R Ku)  (strip w)                                              lqr.jl:170
@@ -296,7 +305,10 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         {
             double po[T][2];
 #pragma unroll
-            for (int j = 0; j < T; j++) { po[j][0] = ok0[j] ? po_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? po_c[8 * j + 1] : acc[j][1]; }
+            for (int j = 0; j < T; j++) {
+                if constexpr (STAGE == 2) { po[j][0] = ok0[j] ? pold[j][0] : acc[j][0]; po[j][1] = ok1[j] ? pold[j][1] : acc[j][1]; }
+                else { po[j][0] = ok0[j] ? po_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? po_c[8 * j + 1] : acc[j][1]; }
+            }
 #pragma unroll
             for (int j = 0; j < T; j++) { const double d0 = po[j][0] - acc[j][0], d1 = po[j][1] - acc[j][1]; nd = fma(d0, d0, nd); nd = fma(d1, d1, nd); }
         }
@@ -325,16 +337,16 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     if (tid == 0) { kexit[s] = k; iters[s] = it; }
 }
 
-size_t dmma_smem_bytes(int n, int T, int stage) {
+size_t dmma_smem_bytes(int n, int T, int stage, bool nu1 = false) {
     const int LD = dmma_ld(n);
-    return ((size_t)(stage == 2 ? 5 : stage == 1 ? 3 : 2) * n * LD + 3 * 8 * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
+    return ((size_t)(stage == 2 ? 4 : stage == 1 ? 3 : 2) * n * LD + 3 * (nu1 ? 1 : 8) * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
 }
 
 template <int T, bool NU1, int STAGE>
 int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D, long long stride_s_A,
                 long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku, int* kexit, int* iters, double* ws,
                 long long ws_stride, cudaStream_t stream) {
-    const size_t smem = dmma_smem_bytes(n, T, STAGE);
+    const size_t smem = dmma_smem_bytes(n, T, STAGE, NU1);
     CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T, NU1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     riccati_sweep_dmma_kernel<T, NU1, STAGE><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
                                                              iters, ws, ws_stride);
