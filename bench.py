@@ -171,6 +171,13 @@ def cpu_reference_run(steps, warmup, sample_systems=None):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -189,12 +196,12 @@ def main():
         if rank != 0:
             return
         value, cores, sample, ms = cpu_reference_run(K, W)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "closed-loop sim steps/s", "value": value, "unit": "sim steps/s", "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference algorithm (Julia reference not runnable here)"},
             "cpu_baseline": {"value": value, "unit": "sim steps/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "sim steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": value, "unit": "sim steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     import torch
@@ -343,7 +350,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_reference_run(1, 0)
             out["cpu_baseline"] = {"value": v, "unit": "sim steps/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
