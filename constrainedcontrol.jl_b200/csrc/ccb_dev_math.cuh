@@ -83,6 +83,40 @@ __device__ __forceinline__ void row_eval(int kind, V3 pr, V3 p1, V3 p2, Q4 qoff,
     }
 }
 
+// The same row, split for kernels whose lanes hold rows of different kinds (K1r, K1m): the pose-only part that every row of a
+// joint shares is formed by all lanes without divergence, then each lane finishes its own row.
+struct JointFrame { V3 c; Q4 qab, qe; };   // c = R_a^T (x_b + R_b p2 - x_a),  qab = q_a^-1 q_b,  qe = qab q_off^-1
+__device__ __forceinline__ JointFrame joint_frame(V3 p2, Q4 qoff, V3 xa, Q4 qa, V3 xb, Q4 qb) {
+    JointFrame f;
+    f.c = qrotT(qa, xb + qrot(qb, p2) - xa);
+    f.qab = qmul(qconj(qa), qb);
+    f.qe = qmul(f.qab, qconj(qoff));
+    return f;
+}
+__device__ __forceinline__ void row_finish(int kind, V3 pr, V3 p1, V3 p2, Q4 qoff, Q4 qa, Q4 qb, const JointFrame& f, bool jac, double& g, V3& Gax,
+                                           V3& Gap, V3& Gbx, V3& Gbp) {
+    if (kind == 0) {
+        g = dot(pr, f.c - p1);
+        if (jac) {
+            V3 n = qrot(qa, pr);
+            V3 m = qrotT(qb, n);
+            Gbx = n;
+            Gbp = -2.0 * cross(m, p2);
+            Gax = -n;
+            Gap = 2.0 * cross(pr, f.c);
+        }
+    } else {
+        g = pr.x * f.qe.x + pr.y * f.qe.y + pr.z * f.qe.z;
+        if (jac) {
+            Q4 e = {0.0, pr.x, pr.y, pr.z};
+            Gbx = {0.0, 0.0, 0.0};
+            Gax = {0.0, 0.0, 0.0};
+            Gbp = qvec(qmul(qmul(qconj(f.qab), e), qoff));
+            Gap = -qvec(qmul(e, qconj(f.qe)));
+        }
+    }
+}
+
 // inverse of a row-major 3x3 by the adjugate
 __device__ __forceinline__ void inv3(const double* A, double* Ai) {
     double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];

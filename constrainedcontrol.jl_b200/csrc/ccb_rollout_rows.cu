@@ -362,7 +362,12 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             }
             double g;
             V3 Gax, Gap, Gbx, Gbp;
-            row_eval(kind, pr, ld3(cj), ld3(cj + 3), ld4(cj + 6), xa3, qa3, v3(p3[0], p3[1], p3[2]), Q4{p3[3], p3[4], p3[5], p3[6]}, jac, g, Gax, Gap, Gbx, Gbp);
+            {
+                const V3 p1 = ld3(cj), p2 = ld3(cj + 3);
+                const Q4 qoff = ld4(cj + 6), qb3 = Q4{p3[3], p3[4], p3[5], p3[6]};
+                const JointFrame jf = joint_frame(p2, qoff, xa3, qa3, v3(p3[0], p3[1], p3[2]), qb3);      // shared by the rows of the joint: no divergence
+                row_finish(kind, pr, p1, p2, qoff, qa3, qb3, jf, jac, g, Gax, Gap, Gbx, Gbp);
+            }
             if (rowpad) g = 0.0;
             ss = fma(g, g, ss);
             rhs = g;
