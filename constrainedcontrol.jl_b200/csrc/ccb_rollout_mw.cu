@@ -24,7 +24,7 @@ constexpr int kGS = 62;   // doubles per joint in the knot-row table: 5 rows x 1
 constexpr int kCS = 24;   // constants per joint: p1 3, p2 3, qoff 4, axis 3, J 9, mass 1 (+1)
 
 #ifndef K1M_MAXREG
-#define K1M_MAXREG 128
+#define K1M_MAXREG 255
 #endif
 
 __device__ __forceinline__ double rcp_nr(double x) {
