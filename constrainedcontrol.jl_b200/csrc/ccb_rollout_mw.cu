@@ -52,7 +52,9 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
     double* red = pivb + 24;                    // [5 nj]     per-row partials
     double* red2 = red + 5 * nj;                // [nj]       per-joint partials
     double* xu = red2 + nj;                     // [nj + 1]   joint inputs
-    int* jorder = reinterpret_cast<int*>(xu + nj + 1);   // [nj] joint at chain position
+    double* ured = xu + nj + 1;                 // [8][5 nj]  control-law partials (up to 8 inputs per round)
+    double* ured2 = ured + 40 * nj;             // [8][nj]
+    int* jorder = reinterpret_cast<int*>(ured2 + 8 * nj);   // [nj] joint at chain position
 
     const int q = threadIdx.x;
     const int sys = blockIdx.x;
@@ -217,14 +219,40 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
                     else if (r == 2) dz = qvec(qmul(qconj(ldg4(d + 3)), Q4{z[3], z[4], z[5], z[6]}));
                     else dz = v3(z[10] - __ldg(d + 10), z[11] - __ldg(d + 11), z[12] - __ldg(d + 12));
                 }
-                for (int i = 0; i < C.nu; i++) {
-                    double part = 0.0;
-                    if (lane_ok && r < 4) {
-                        const double* Kr = K + (size_t)i * n + 12 * b + 3 * r;
-                        part = fma(__ldg(Kr), dz.x, fma(__ldg(Kr + 1), dz.y, __ldg(Kr + 2) * dz.z));
+                // all inputs at once: the gain rows are fetched with independent loads and reduced with ONE pair of barriers
+                // (rows -> joints -> system, fixed order), up to 8 inputs per round
+                for (int i0 = 0; i0 < C.nu; i0 += 8) {
+                    const int ni = min(8, C.nu - i0);
+                    double part[8];
+#pragma unroll
+                    for (int ii = 0; ii < 8; ii++) {
+                        part[ii] = 0.0;
+                        if (ii < ni && lane_ok && r < 4) {
+                            const double* Kr = K + (size_t)(i0 + ii) * n + 12 * b + 3 * r;
+                            part[ii] = fma(__ldg(Kr), dz.x, fma(__ldg(Kr + 1), dz.y, __ldg(Kr + 2) * dz.z));
+                        }
                     }
-                    const double tot = sys_sum(part);
-                    if (lane_ok && r == 0 && __ldg(C.eqc + i) == jt) u += __ldg(Fd + i) - tot;
+                    if (lane_ok) {
+#pragma unroll
+                        for (int ii = 0; ii < 8; ii++) if (ii < ni) ured[ii * 5 * nj + q] = part[ii];
+                    }
+                    __syncthreads();
+                    if (lane_ok && r == 0) {
+                        for (int ii = 0; ii < ni; ii++) {
+                            const double* rp = ured + ii * 5 * nj + q;
+                            ured2[ii * nj + pos] = ((rp[0] + rp[1]) + (rp[2] + rp[3])) + rp[4];
+                        }
+                    }
+                    __syncthreads();
+                    if (lane_ok && r == 0) {
+                        for (int ii = 0; ii < ni; ii++) {
+                            if (__ldg(C.eqc + i0 + ii) != jt) continue;
+                            double tot = 0.0;
+                            for (int p = 0; p < nj; p++) tot += ured2[ii * nj + p];
+                            u += __ldg(Fd + i0 + ii) - tot;
+                        }
+                    }
+                    __syncthreads();
                 }
             }
         }
@@ -549,7 +577,7 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
     const int nj = M.nj;
     const int threads = ((5 * nj + 31) / 32) * 32;
     const size_t doubles = (size_t)nj * kGS + (size_t)nj * kCS + (size_t)nj * 8 + (size_t)nj * 6 + (size_t)nj * 9 + (5 * nj + 5) + (size_t)nj * 6 + 24 +
-                           5 * nj + nj + (nj + 1);
+                           5 * nj + nj + (nj + 1) + 40 * nj + 8 * nj;
     const size_t smem = doubles * sizeof(double) + (size_t)nj * sizeof(int) + 16;
     if (smem > 227 * 1024) { set_error("mechanism too large for the multi-warp rows kernel"); return CCB_E_UNSUPPORTED; }
 #define CCB_MW_LAUNCH(NJT)                                                                                                    \
