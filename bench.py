@@ -140,6 +140,54 @@ def synthesis_bench(cc, torch, dev, peaks):
     return out
 
 
+def tracking_bench(cc, torch, dev):
+    """BASELINE config 3 (lqr_sawyer ... + trackingLQR rollout, batch 1024): 64 reference trajectories of the Sawyer arm (open-loop
+    sinusoidal joint torques, 2000 steps, recorded on the GPU) -> TrackingLQR synthesis about each (device-resident tables) -> 16 perturbed
+    closed-loop rollouts per trajectory (torque amplitudes scaled to the link inertias so that |w| stays far below 2/dt)."""
+    golden = os.path.join(ROOT, "tests", "golden", "sawyer_arm.json")
+    mech, cfg = cc.examples.sawyer(golden)
+    NT, N, PER = 64, 2000, 16
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, (NT, 7)) * np.array([0.05, 0.05, 0.02, 0.02, 0.005, 0.005, 0.0005]); f = rng.integers(1, 4, (NT, 7))
+    k = np.arange(N)[None, :, None]
+    U = a[:, None, :] * np.sin(2 * np.pi * f[:, None, :] * k / 2000.0)
+    cc.urdf.zero_configuration(mech)
+    st0 = mech.batch_states(NT)
+    sto, _, status = cc.simulate(mech, N * mech.dt, cc.OpenLoop(mech, cfg["eqcids"], U), record=True, states=st0, device=dev, return_status=True)
+    assert np.all(status > 0)
+    synth_wall, tl = None, None
+    for _ in range(2):      # the first call pays one-off costs (module load, 20+ GB of scratch): report the second
+        if tl is not None:
+            tl.invalidate()
+        t0 = time.time()
+        tl = cc.TrackingLQR(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"], device=dev)
+        synth_wall = time.time() - t0
+    ph = cc.synth.phase_ms()
+    B = NT * PER
+    stp = np.repeat(st0, PER, axis=0)
+    for s_ in range(B):
+        cc.urdf.zero_configuration(mech, {i: rng.uniform(-0.005, 0.005) for i in range(7)})
+        stp[s_] = mech.state_vector()
+    cc.urdf.zero_configuration(mech)
+    tl.replicate(PER)
+    batch = cc.Batch(mech, B, dev)
+    stream = torch.cuda.ExternalStream(batch.stream(), device=dev)
+    best = None
+    for _ in range(2):
+        batch.set_state(stp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); batch.simulate_device(tl, 1, N); e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    fin = batch.get_state()
+    err = float(np.abs(fin[:, :, 0:3] - np.repeat(sto.data[-1], PER, axis=0)[:, :, 0:3]).max())
+    return {"workload": "lqr_sawyer TrackingLQR: 64 reference trajectories x 2000 steps, 16 perturbed closed-loop rollouts each (1024 systems)",
+            "synthesis_device_ms": sum(ph.values()), "synthesis_phase_ms": ph, "synthesis_e2e_s": synth_wall,
+            "linearisations_per_s_device": NT * (N - 1) / (sum(ph.values()) * 1e-3),
+            "rollout_sim_steps_per_s": B * N / (best * 1e-3), "rollout_ms": best, "final_tracking_error_m": err}
+
+
 def cpu_reference_run(steps, warmup, sample_systems=None):
     """the reference arm / cpu_baseline: CPU restatement on all host cores, bounded sample of the same workload"""
     import ccb200 as cc
@@ -331,6 +379,10 @@ def main():
                 out["synthesis"] = synthesis_bench(cc, torch, dev, fp)
             except Exception as e:   # the headline line must still print
                 out["synthesis"] = {"error": repr(e)}
+            try:
+                out["tracking"] = tracking_bench(cc, torch, dev)
+            except Exception as e:
+                out["tracking"] = {"error": repr(e)}
             try:   # the same rollout kernel at a batch that fills the machine (north_star: ">= 4096-system batches")
                 Bbig = 16 * BATCH
                 big = cc.Batch(mech, Bbig, dev)
