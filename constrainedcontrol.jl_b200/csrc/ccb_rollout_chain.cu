@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(32) rollout_chain_kernel(const DevMech M, cons
                 it_used = n;
                 const double nd = alpha * full;
                 if (tiny || (nd < A.eps && normf1 < A.eps)) done = true;
+                if (!(normf1 == normf1)) { done = true; failed = true; }   // NaN residual: no iterate can recover, the step has failed
                 normf0 = normf1;
             }
         }

@@ -525,6 +525,7 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
                 normf0 = nfe;
                 if (done || n >= A.newton_iter) break;
             }
+            if (!(nfe == nfe)) break;      // NaN residual (accepted by lineSearch! like the reference: NaN >= x is false): nothing can recover, step failed
             solve();
             n++;
             double sd = lane_ok ? dl * dl : 0.0;

@@ -522,6 +522,9 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
                 }
             }
             first = false;
+            // NaN residual (e.g. |w| beyond 2/dt): lineSearch! has accepted it like the reference does (NaN >= x is false), no later iterate can
+            // recover, so the step is abandoned as failed instead of burning newtonIter x lineIter evaluations
+            if (!(nfe == nfe) && !done && !pending) { done = true; out_of_iters = true; want_solve = false; }
             if (!__any_sync(0xffffffffu, want_solve)) {
                 if (!__any_sync(0xffffffffu, pending)) break;
                 continue;

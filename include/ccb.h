@@ -148,7 +148,8 @@ int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t se
  * ConstrainedDynamics.jl time loop) for every system of the batch:
  *   for k = k0 .. k0+steps-1 : record, control!(k), applyFτ!, newton!(ε, newtonIter, lineIter), updatestate!
  * storage (host, may be NULL): [steps][B][nb][13] = (xc,qc,vc,ωc) at the start of each step (Storage{T,N}).
- * status (host, may be NULL): [B] total Newton iterations, negated if any step failed to converge.
+ * status (host, may be NULL): [B] total Newton iterations, negated if any step failed to converge.  A step whose residual has become NaN
+ * (e.g. |ω| beyond 2/Δt) is abandoned at once -- it is flagged like a step that ran into newtonIter, its state is NaN as in the reference.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct ccb_sim_opts {
     double eps;           /* newton! ε, default 1e-10 */
