@@ -25,7 +25,8 @@ __host__ __device__ inline int dmma_ld(int n) { return (n % 16 == 4 || n % 16 ==
 
 // NU1: scalar input (nu == 1): the nu x nu solve is a division and the generic elimination is compiled out (it costs ~128 registers).
 // STAGE (time-invariant problems): 2 = Ã, Q and the previous P also live in shared memory, so an iteration touches global memory only
-// to store the gain row (small n); 1 = only Ã is staged (n <= 84: three n x n matrices fit in 227 KB); 0 = everything streams from L2.
+// to store the gain row (small n); 1 = the previous P is kept in a third shared-memory matrix instead of a global round trip (72 <= n <= 84:
+// three n x n matrices fit in 227 KB); 0 = Ã, Q stream from L2 and the previous P goes through the global copy.
 #ifndef K4_MINB_NUM
 #define K4_MINB_NUM 24   // resident warps per SM the small-problem variants are compiled for (registers = 64 K / (32 * this))
 #endif
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* Sc = Dp + (size_t)n * 8;          // [8][8]   R + D'P D
     double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
     double* red = Rs + 64;                    // [T] partial sums (padded to 16)
-    double* Asm = red + 16;                   // STAGE: [n][LD] Ã
+    double* Asm = red + 16;                   // STAGE == 2: [n][LD] Ã ; STAGE == 1: [n][LD] previous P
     double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE == 2: [n][LD] Q
     double* Pold = Qsm + (STAGE == 2 ? (size_t)n * LD : 0);  // (unused since the previous P of a staged problem is kept in registers)
     __shared__ int brk;
@@ -72,11 +73,12 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
     const double* q_c = STAGE == 2 ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
-    double* po_c = pg_c;                                      // STAGE < 2: the previous P is kept in the global copy for the ‖P - P+‖ test
+    // previous P for the ‖P - P+‖ test: registers (STAGE 2), shared memory (STAGE 1: 72 <= n <= 84) or the global copy (STAGE 0)
+    double* po_c = STAGE == 1 ? Asm + (size_t)ra * LD + 2 * t4 : pg_c;
     (void)Pold;
 
     for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
-    if (STAGE) {
+    if (STAGE == 2) {
         const double* A0 = At + s * stride_s_A;
         for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (STAGE == 2) Qsm[(size_t)i * LD + j] = Qs[e]; }
     }
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 DtP[j] = (a0 + a1) + (a2 + a3);
             }
             __syncthreads();
-            const size_t lda = STAGE ? (size_t)LD : (size_t)n;
-            const double* Ab = STAGE ? Asm : Ak;
+            const size_t lda = STAGE == 2 ? (size_t)LD : (size_t)n;
+            const double* Ab = STAGE == 2 ? Asm : Ak;
             for (int j = tid; j < n; j += NT) {                       // (B) rhs[j] = sum_k DtP[k] Ã[k][j]
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 const double* ac = Ab + j;
@@ -148,8 +150,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             {
                 const int j0 = 8 * w, cb = min(j0 + g, n - 1);
                 double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-                const size_t lda = STAGE ? (size_t)LD : (size_t)n;
-                const double* ag = (STAGE ? Asm : Ak) + (size_t)t4 * lda + cb;
+                const size_t lda = STAGE == 2 ? (size_t)LD : (size_t)n;
+                const double* ag = (STAGE == 2 ? Asm : Ak) + (size_t)t4 * lda + cb;
                 const double* dr = DtP + g * LD + t4;
                 int k0 = 0;
                 for (; k0 + 16 <= n; k0 += 16) {                              // four independent loads in flight
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         // ---- (D) Abar = Ã - D Ku  (strip w; rank-8 update of Ã read from global in C layout)          lqr.jl:169
         double acc[T][2];
         {
-            const double* a_c = STAGE ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
+            const double* a_c = STAGE == 2 ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
 #pragma unroll
             for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? a_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? a_c[8 * j + 1] : 0.0; }
             if (NU1) {
@@ -369,7 +371,7 @@ int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, con
                               int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
     const int T = (n + 7) / 8;
     const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
-    const bool stage_a = stride_t_A == 0 && !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;   // 72 <= n <= 84: Ã only (+2 %; for smaller n the extra shared memory costs more residency than it saves)
+    const bool stage_a = !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
 #define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream
 #define CCB_DMMA_CASE(TT)                                                                      \
     case TT:                                                                                   \
