@@ -131,10 +131,12 @@ def synthesis_bench(cc, torch, dev, peaks):
         dev_s = sum(ph.values()) * 1e-3
         # dense flops of one iteration of dlqr AS WRITTEN in lqr.jl:151-170 (loop invariants hoisted),
         #   F = 4 n^3 + 6 n^2 q + 2/3 q^3 + 2 q^2 n + 2 mu n^2 ,  q = mu + m_lambda  -- the algorithmic work of the reference per iteration;
-        # the kernel reaches the same gains with the constraint-projected recursion, which EXECUTES only 4 n^3 + 8 mu n^2 of them.
+        # the kernel reaches the same gains with the constraint-projected recursion and forms only the tiles (w, (w+d) mod T), d <= T/2, of the
+        # symmetric P+, so it EXECUTES about 2 n^3 (P Abar) + 2 n^3 (T/2+1)/T (Abar' W) + 8 mu n^2 of them.
         q = nu + mech.ml
         F_ref = 4.0 * n ** 3 + 6.0 * n * n * q + (2.0 / 3.0) * q ** 3 + 2.0 * q * q * n + 2.0 * nu * n * n
-        F_exec = 4.0 * n ** 3 + 8.0 * nu * n * n
+        T = (n + 7) // 8
+        F_exec = 2.0 * n ** 3 * (1.0 + (T // 2 + 1) / T) + 8.0 * nu * n * n
         tf = S * iters * F_ref / (ph["sweep"] * 1e-3) / 1e12
         tf_exec = S * iters * F_exec / (ph["sweep"] * 1e-3) / 1e12
         peak = peaks.get("dmma_m8n8k4_tflops")

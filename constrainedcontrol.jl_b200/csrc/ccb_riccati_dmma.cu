@@ -69,6 +69,18 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     bool ok0[T], ok1[T];                                      // which of my two C elements of tile column j exist
 #pragma unroll
     for (int j = 0; j < T; j++) { cbj[j] = min(8 * j + g, n - 1); ok0[j] = row_ok && 8 * j + 2 * t4 < n; ok1[j] = row_ok && 8 * j + 2 * t4 + 1 < n; }
+    // P+ is symmetric: strip w only forms the tiles (w, (w + d) mod T), d = 0 .. T/2 (every unordered pair of strips once) and mirrors them
+    constexpr int H = T / 2 + 1;
+    int jd[H], cbd[H];
+    bool use_d[H], okd0[H], okd1[H];
+#pragma unroll
+    for (int d = 0; d < H; d++) {
+        jd[d] = (w + d >= T) ? w + d - T : w + d;
+        use_d[d] = (T % 2 == 1) || d < T / 2 || w < T / 2;        // even T: the distance-T/2 pairs would be formed twice
+        cbd[d] = min(8 * jd[d] + g, n - 1);
+        okd0[d] = use_d[d] && row_ok && 8 * jd[d] + 2 * t4 < n;
+        okd1[d] = use_d[d] && row_ok && 8 * jd[d] + 2 * t4 + 1 < n;
+    }
     double* ps_c = Ps + (size_t)ra * LD + 2 * t4;             // my C elements of tile column j are at [8 j], [8 j + 1]
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
@@ -260,11 +272,14 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             }
         }
         __syncthreads();
-        double pold[STAGE == 2 ? T : 1][2];
+        double pold[STAGE == 2 ? H : 1][2];
+        if constexpr (STAGE == 2) {                                      // small staged problems: previous P of my tiles stays in registers
 #pragma unroll
-        for (int j = 0; j < T; j++) {                                    // old P -> registers / global copy (for the ‖P - P+‖ test), W -> shared
-            if constexpr (STAGE == 2) {                                  // small staged problems: previous P stays in registers
-                pold[j][0] = ps_c[8 * j]; pold[j][1] = ps_c[8 * j + 1];
+            for (int d = 0; d < H; d++) { pold[d][0] = ps_c[8 * jd[d]]; pold[d][1] = ps_c[8 * jd[d] + 1]; }
+        }
+#pragma unroll
+        for (int j = 0; j < T; j++) {                                    // old P -> shared / global copy (for the ‖P - P+‖ test), W -> shared
+            if constexpr (STAGE == 2) {
                 if (ok0[j]) ps_c[8 * j] = acc[j][0];
                 if (ok1[j]) ps_c[8 * j + 1] = acc[j][1];
             } else {
@@ -273,16 +288,18 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             }
         }
         __syncthreads();
-        // ---- (F) P+ = Q + Abar' W + Ku' (R Ku)  (strip w)                                              lqr.jl:170
+        // ---- (F) P+ = Q + Abar' W + Ku' (R Ku): tiles (w, jd[d]) only, then mirrored                    lqr.jl:170
+        double accF[H][2];
 #pragma unroll
-        for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? q_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? q_c[8 * j + 1] : 0.0; }
+        for (int d = 0; d < H; d++) { accF[d][0] = okd0[d] ? q_c[8 * jd[d]] : 0.0; accF[d][1] = okd1[d] ? q_c[8 * jd[d] + 1] : 0.0; }
         {
             const double* arow = As + (size_t)t4 * LD + ra;              // Abar^T fragment
             const double* brow = Ps + (size_t)t4 * LD;                   // W
             for (int k0 = 0; k0 < n; k0 += 4) {
                 const double a = *arow;
 #pragma unroll
-                for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+                for (int d = 0; d < H; d++)
+                    if (use_d[d]) dmma(accF[d][0], accF[d][1], a, brow[cbd[d]]);
                 arow += 4 * LD; brow += 4 * LD;
             }
         }
@@ -290,9 +307,9 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             const double ki = Kk[ra];
             const double* rc = RK + 2 * t4;
 #pragma unroll
-            for (int j = 0; j < T; j++) {
-                if (ok0[j]) acc[j][0] = fma(ki, rc[8 * j], acc[j][0]);
-                if (ok1[j]) acc[j][1] = fma(ki, rc[8 * j + 1], acc[j][1]);
+            for (int d = 0; d < H; d++) {
+                if (okd0[d]) accF[d][0] = fma(ki, rc[8 * jd[d]], accF[d][0]);
+                if (okd1[d]) accF[d][1] = fma(ki, rc[8 * jd[d] + 1], accF[d][1]);
             }
         } else {
 #pragma unroll
@@ -300,19 +317,27 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 const double a = Kk[(k0 + t4) * LD + ra];                // Ku^T fragment
                 const double* brow = RK + (k0 + t4) * LD;
 #pragma unroll
-                for (int j = 0; j < T; j++) dmma(acc[j][0], acc[j][1], a, brow[cbj[j]]);
+                for (int d = 0; d < H; d++)
+                    if (use_d[d]) dmma(accF[d][0], accF[d][1], a, brow[cbd[d]]);
             }
         }
-        double nd = 0.0;                                                 // ‖P - P+‖_F^2 over my fragments (old P from the global copy)
-        {
-            double po[T][2];
+        {   // the diagonal tile is averaged with its own transpose so that P stays EXACTLY symmetric: rounding-level asymmetry confined to
+            // the diagonal tiles is amplified by this recursion on stiff problems (8-pendulum, N = 300: gains off by O(1))
+            const int src0 = (2 * t4) * 4 + (g >> 1), src1 = (2 * t4 + 1) * 4 + (g >> 1);
+            const double u00 = __shfl_sync(0xffffffffu, accF[0][0], src0), u01 = __shfl_sync(0xffffffffu, accF[0][1], src0);
+            const double u10 = __shfl_sync(0xffffffffu, accF[0][0], src1), u11 = __shfl_sync(0xffffffffu, accF[0][1], src1);
+            accF[0][0] = 0.5 * (accF[0][0] + ((g & 1) ? u01 : u00));
+            accF[0][1] = 0.5 * (accF[0][1] + ((g & 1) ? u11 : u10));
+        }
+        double nd = 0.0;                                                 // ‖P - P+‖_F^2: off-diagonal tiles stand for their mirror image too
 #pragma unroll
-            for (int j = 0; j < T; j++) {
-                if constexpr (STAGE == 2) { po[j][0] = ok0[j] ? pold[j][0] : acc[j][0]; po[j][1] = ok1[j] ? pold[j][1] : acc[j][1]; }
-                else { po[j][0] = ok0[j] ? po_c[8 * j] : acc[j][0]; po[j][1] = ok1[j] ? po_c[8 * j + 1] : acc[j][1]; }
-            }
-#pragma unroll
-            for (int j = 0; j < T; j++) { const double d0 = po[j][0] - acc[j][0], d1 = po[j][1] - acc[j][1]; nd = fma(d0, d0, nd); nd = fma(d1, d1, nd); }
+        for (int d = 0; d < H; d++) {
+            double p0, p1;
+            if constexpr (STAGE == 2) { p0 = pold[d][0]; p1 = pold[d][1]; }
+            else { p0 = okd0[d] ? po_c[8 * jd[d]] : 0.0; p1 = okd1[d] ? po_c[8 * jd[d] + 1] : 0.0; }
+            const double d0 = okd0[d] ? p0 - accF[d][0] : 0.0, d1 = okd1[d] ? p1 - accF[d][1] : 0.0;
+            const double wgt = d == 0 ? 1.0 : 2.0;
+            nd = fma(wgt * d0, d0, nd); nd = fma(wgt * d1, d1, nd);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
@@ -324,9 +349,10 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             brk = sqrt(tot) < 1e-5;                                      // lqr.jl:172
         }
 #pragma unroll
-        for (int j = 0; j < T; j++) {                                    // lqr.jl:176  Pk = Pkp1
-            if (ok0[j]) ps_c[8 * j] = acc[j][0];
-            if (ok1[j]) ps_c[8 * j + 1] = acc[j][1];
+        for (int d = 0; d < H; d++) {                                    // lqr.jl:176  Pk = Pkp1: my tiles and their transposes
+            const int c0 = 8 * jd[d] + 2 * t4;
+            if (okd0[d]) { ps_c[8 * jd[d]] = accF[d][0]; if (d > 0) Ps[(size_t)c0 * LD + ra] = accF[d][0]; }
+            if (okd1[d]) { ps_c[8 * jd[d] + 1] = accF[d][1]; if (d > 0) Ps[(size_t)(c0 + 1) * LD + ra] = accF[d][1]; }
         }
         __syncthreads();
         if (brk) break;

@@ -42,13 +42,14 @@ def test_c3_npendulum8_rollout_and_gains(cc, orc):
     eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
     zd = zd_of(mech, cfg)
     Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
-    # gains: the Riccati recursion of the upright 8-pendulum amplifies rounding (P ~ 1e7..1e11): two literal CPU implementations
-    # differ by ~1e-6, so the bound here is that floor, not 1e-9
+    # gains: the Riccati recursion of the upright 8-pendulum amplifies rounding (P ~ 1e7..1e11, gains ~1e6): literal CPU implementations
+    # that differ only in summation order agree to ~2e-9 at N = 300, and any rounding-level asymmetry left in P is amplified to O(1)
+    # (the kernel keeps P exactly symmetric) -- so the bound here is 1e-7, not 1e-9
     out = cc.lqr_synthesize(mech, zd[None], np.zeros((1, 1)), eqc_idx, Qd, Rd, 300)
     lin = om.linearize(zd, [0.0], eqc_idx)
     ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd, Rd, 300)
     assert out["kexit"][0] == ref["kexit"]
-    assert rel_err(out["Ku"][0], ref["Ku"]) < 1e-4
+    assert rel_err(out["Ku"][0], ref["Ku"]) < 1e-7
     # closed loop with THE SAME gain table in both: states to 1e-9 over 150 steps (K1c: one lane per joint, 9 joints)
     K = out["Ku"][0]
     B = 12

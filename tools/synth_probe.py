@@ -24,6 +24,7 @@ for item in spec.split(";"):
     ph = cc.synth.phase_ms()
     n = 12 * mech.nb; nu = len(eqc_idx)
     iters = float(o["iters"].mean())
-    flops = S * iters * (4.0 * n ** 3 + 8.0 * nu * n * n)
+    T = (n + 7) // 8                 # executed flops: P Abar in full, the symmetric P+ as (T/2+1) of T tile columns per strip
+    flops = S * iters * (2.0 * n ** 3 * (1.0 + (T // 2 + 1) / T) + 8.0 * nu * n * n)
     print(f"{name} n={n} nu={nu} S={S} N={N} iters={iters:.0f}: lin {ph['linearize']:.2f} ms, project {ph['project']:.2f} ms, sweep {ph['sweep']:.2f} ms "
           f"-> {S / (sum(ph.values()) * 1e-3):.0f} synth/s device, {S / wall:.0f} e2e; sweep {flops / (ph['sweep'] * 1e-3) / 1e12:.2f} TFLOP/s", flush=True)
