@@ -152,6 +152,28 @@ def synthesis_bench(cc, torch, dev, peaks):
     return out
 
 
+def are_bench(cc):
+    """util.jl's dare / care for batches of dense problems (K5): problems/s, device time from the library's phase timer"""
+    out = {}
+    rng = np.random.default_rng(5)
+    for name, kind, n, m, S in (("dare_n24", cc.util.DISCRETE, 24, 1, 4096), ("care_n24", cc.util.CONTINUOUS, 24, 1, 4096), ("dare_n84", cc.util.DISCRETE, 84, 7, 1024)):
+        A = rng.standard_normal((S, n, n)) / np.sqrt(n) * 1.05
+        if kind == cc.util.CONTINUOUS:
+            A -= 0.5 * np.eye(n)
+        Bm = rng.standard_normal((S, n, m)); Q = np.broadcast_to(np.eye(n), (S, n, n)); R = np.broadcast_to(np.eye(m), (S, m, m))
+        best = None
+        for rep in range(2):
+            t0 = time.time()
+            K, info = cc.util.are_solve(kind, A, Bm, Q, R, want_X=False, want_K=True, info=True)
+            wall = time.time() - t0
+            ms = cc.synth.phase_ms()["sweep"]
+            if best is None or ms < best[0]:
+                best = (ms, wall)
+        out[name] = {"batch": S, "n": n, "m": m, "problems_per_s_device": S / (best[0] * 1e-3), "problems_per_s_e2e": S / best[1],
+                     "doublings_mean": float(info["iters"].mean()), "converged": int((info["status"] == 0).sum())}
+    return out
+
+
 def tracking_bench(cc, torch, dev):
     """BASELINE config 3 (lqr_sawyer ... + trackingLQR rollout, batch 1024): 64 reference trajectories of the Sawyer arm (open-loop
     sinusoidal joint torques, 2000 steps, recorded on the GPU) -> TrackingLQR synthesis about each (device-resident tables) -> 16 perturbed
@@ -395,6 +417,10 @@ def main():
                 out["tracking"] = tracking_bench(cc, torch, dev)
             except Exception as e:
                 out["tracking"] = {"error": repr(e)}
+            try:
+                out["are"] = are_bench(cc)
+            except Exception as e:
+                out["are"] = {"error": repr(e)}
             try:   # the same rollout kernel at a batch that fills the machine (north_star: ">= 4096-system batches")
                 Bbig = 16 * BATCH
                 big = cc.Batch(mech, Bbig, dev)

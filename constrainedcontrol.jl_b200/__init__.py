@@ -6,7 +6,7 @@ Host-side description modules import without the native library; every compute e
 the C-ABI shared library (csrc/libccb.so) and fails loudly when it is missing (no CPU fallback).
 """
 from .mechanism import *  # noqa: F401,F403
-from . import mechanism, examples, _lib, control, synth, urdf, dist  # noqa: F401
+from . import mechanism, examples, _lib, control, synth, urdf, dist, util  # noqa: F401
 from ._lib import CcbError, device_count  # noqa: F401
 from .control import LQR, TrackingLQR, PID, OpenLoop, Controller, Storage, Batch, simulate, handle, blockdiag  # noqa: F401
 from .synth import linearsystem, dlqr, lqr_synthesize, tracking_synthesize  # noqa: F401

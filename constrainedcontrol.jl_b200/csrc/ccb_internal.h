@@ -148,6 +148,10 @@ int launch_rollout_chain(const DevMech& M, const DevCtrl& C, const SimArgs& a, c
 int rollout_smem_bytes(const DevMech& M, int lanes);
 int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
 bool mw_kernel_eligible(const DevMech& M);
+// K5 (ccb_are.cu): kind 0 DARE, 1 CARE; device pointers; ws >= S * are_ws_doubles(n) doubles
+size_t are_ws_doubles(int n);
+int are_sda_device(int kind, int S, int n, int m, const double* A, const double* B, const double* Q, const double* R, double tol, int maxit, double* X,
+                   double* K, int* iters, int* status, double* ws, cudaStream_t stream);
 int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
 
 }  // namespace ccb

@@ -166,6 +166,36 @@ int ccb_dlqr(int32_t device, int32_t S, int32_t n, int32_t nu, int32_t ml, int32
     return CCB_OK;
 }
 
+// dare / care / dlqr / lqr of src/util/util.jl:1-49 for S independent problems (K5, ccb_are.cu)
+int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m, const double* A, const double* B, const double* Q, const double* R,
+                  double* X, double* K, int32_t* iters, int32_t* status) {
+    if ((kind != CCB_ARE_DISCRETE && kind != CCB_ARE_CONTINUOUS) || S < 1 || n < 1 || m < 1 || m > n || !A || !B || !Q || !R || (!X && !K)) {
+        set_error("ccb_are_solve: bad arguments (kind, S >= 1, 1 <= m <= n, A, B, Q, R and at least one of X, K)");
+        return CCB_E_INVALID;
+    }
+    CCB_TRY(check_device(device, "ccb_are_solve"));
+    Scratch sc;
+    double *d_A, *d_B, *d_Q, *d_R, *d_X = nullptr, *d_K = nullptr, *d_ws;
+    int *d_it, *d_st;
+    const size_t nn = (size_t)n * n;
+    CCB_TRY(sc.put(&d_A, A, S * nn)); CCB_TRY(sc.put(&d_B, B, (size_t)S * n * m)); CCB_TRY(sc.put(&d_Q, Q, S * nn)); CCB_TRY(sc.put(&d_R, R, (size_t)S * m * m));
+    if (X) CCB_TRY(sc.get(&d_X, S * nn));
+    if (K) CCB_TRY(sc.get(&d_K, (size_t)S * m * n));
+    CCB_TRY(sc.get(&d_it, (size_t)S)); CCB_TRY(sc.get(&d_st, (size_t)S));
+    CCB_TRY(sc.get(&d_ws, are_ws_doubles(n) * sizeof(double) <= 200 * 1024 ? (size_t)1 : (size_t)S * are_ws_doubles(n)));
+    PhaseTimer pt;
+    pt.mark(0); pt.mark(1); pt.mark(2);
+    CCB_TRY(are_sda_device(kind, S, n, m, d_A, d_B, d_Q, d_R, 1e-15, 64, d_X, d_K, d_it, d_st, d_ws, 0));
+    pt.mark(3);
+    CCB_CUDA(cudaDeviceSynchronize());
+    pt.finish(false);
+    if (X) CCB_CUDA(cudaMemcpy(X, d_X, S * nn * sizeof(double), cudaMemcpyDeviceToHost));
+    if (K) CCB_CUDA(cudaMemcpy(K, d_K, (size_t)S * m * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (iters) CCB_CUDA(cudaMemcpy(iters, d_it, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    if (status) CCB_CUDA(cudaMemcpy(status, d_st, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    return CCB_OK;
+}
+
 int ccb_synth_phase_ms(double out[4]) {
     for (int i = 0; i < 4; i++) out[i] = g_phase_ms[i];
     return CCB_OK;

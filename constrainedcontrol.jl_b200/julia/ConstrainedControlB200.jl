@@ -319,4 +319,34 @@ function simulate!(batch::BatchStates, Δt::Real, tend::Real, controller::Union{
     return record ? storage : nothing
 end
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# Algebraic-Riccati utilities (reference src/util/util.jl) on the device: same names and argument order, matrices may carry a
+# trailing batch dimension (n, n, S).  Julia is column-major, the ABI row-major: every matrix goes through `permutedims`.
+# ---------------------------------------------------------------------------------------------------------------------------
+rowmajor(M::AbstractMatrix) = reshape(permutedims(Matrix{Float64}(M)), size(M, 2), size(M, 1), 1)
+rowmajor(M::AbstractArray{<:Real,3}) = permutedims(Array{Float64,3}(M), (2, 1, 3))
+
+function are_solve(kind::Integer, A, B, Q, R; wantX = true, wantK = false, device = 0)
+    Ar, Br, Qr, Rr = rowmajor(A), rowmajor(B), rowmajor(Q), rowmajor(R)
+    n = size(Ar, 1); m = size(Br, 1); S = maximum(size.((Ar, Br, Qr, Rr), 3))
+    rep(M) = size(M, 3) == S ? M : repeat(M, 1, 1, S)
+    Ar, Br, Qr, Rr = rep(Ar), rep(Br), rep(Qr), rep(Rr)
+    X = wantX ? Array{Float64}(undef, n, n, S) : nothing
+    K = wantK ? Array{Float64}(undef, n, m, S) : nothing          # row-major [S][m][n]
+    iters = zeros(Int32, S); status = zeros(Int32, S)
+    check(ccall((:ccb_are_solve, libccb), Cint,
+                (Int32, Int32, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                device, kind, S, n, m, Ar, Br, Qr, Rr, wantX ? X : C_NULL, wantK ? K : C_NULL, iters, status))
+    any(!=(0), status) && @info "Riccati equation: no stabilising solution found for $(count(!=(0), status)) of $S problems."
+    single = ndims(A) == 2 && ndims(B) <= 2 && ndims(Q) == 2
+    out(M) = single ? permutedims(M[:, :, 1]) : permutedims(M, (2, 1, 3))
+    return wantX && wantK ? (out(X), out(K)) : wantX ? out(X) : out(K)
+end
+
+dare(A, B, Q, R; kw...) = are_solve(0, A, B, Q, R; kw...)                                   # util.jl:1-20
+care(A, B, Q, R; kw...) = are_solve(1, A, B, Q, R; kw...)                                   # util.jl:22-37
+lqr(A, B, Q, R; kw...) = are_solve(1, A, B, Q, R; wantX = false, wantK = true, kw...)        # util.jl:39-43
+dlqr(A, B, Q, R; kw...) = are_solve(0, A, B, Q, R; wantX = false, wantK = true, kw...)       # util.jl:45-49
+dlqr(A, B, Q, R, Δt::Real; kw...) = dlqr(A .* Δt .+ Matrix{Float64}(I, size(A, 1), size(A, 1)), B .* Δt, Q .* Δt, R .* Δt; kw...)   # util.jl:51-59
+
 end # module

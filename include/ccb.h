@@ -219,6 +219,22 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
 int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc, int32_t nu,
                         const double* Q, const double* R, const ccb_sim_opts* opts, ccb_ctrl** out, int32_t* kexit, int32_t* iters);
 
+/* ------------------------------------------------------------------------------------------------
+ * Algebraic Riccati utilities of the reference (src/util/util.jl) for S independent problems, row-major:
+ *   A [S][n][n], B [S][n][m], Q [S][n][n], R [S][m][m]  (1 <= m <= n; Q, R symmetric, R positive definite).
+ *   kind CCB_ARE_DISCRETE:    X = dare(A,B,Q,R)  (util.jl:1-20),   K = dlqr(A,B,Q,R) = (R + B'XB) \ B'XA  (util.jl:45-49)
+ *   kind CCB_ARE_CONTINUOUS:  X = care(A,B,Q,R)  (util.jl:22-37),  K = lqr(A,B,Q,R)  = R \ B'X           (util.jl:39-43)
+ * X [S][n][n] and K [S][m][n]: either may be NULL.  dlqr(A,B,Q,R,Δt) (util.jl:51-59) is the discrete call on
+ * (A Δt + I, B Δt, Q Δt, R Δt): the caller scales.  iters [S] (may be NULL) = doubling iterations; status [S] (may be
+ * NULL): 0 converged, 1 not converged (no stabilising solution within 64 doublings), 2 numerical breakdown.
+ * The device computes the stabilising solution with the structure-preserving doubling algorithm instead of the ordered
+ * (generalised) Schur form of util.jl:16-17,28-29: same matrix, no data-dependent eigenvalue reordering.
+ * ------------------------------------------------------------------------------------------------ */
+#define CCB_ARE_DISCRETE 0
+#define CCB_ARE_CONTINUOUS 1
+int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m, const double* A, const double* B, const double* Q,
+                  const double* R, double* X, double* K, int32_t* iters, int32_t* status);
+
 /* Device time (ms, CUDA events on the launching stream) of the phases of the last ccb_dlqr / ccb_lqr_synthesize /
  * ccb_tracking_synthesize call on the calling thread: out[0] linearisation (K1 knot solve + K2), out[1] constraint projection,
  * out[2] Riccati sweep (K3 / K4), out[3] reserved.  Measurement aid for bench.py (no reference counterpart). */
