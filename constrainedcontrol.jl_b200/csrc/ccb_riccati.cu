@@ -165,6 +165,11 @@ int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, con
                               long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                               int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream);
 
+bool riccati_big_eligible(int n, int nu);
+int riccati_sweep_big_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
+                             long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
+                             int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream);
+
 size_t riccati_project_ws_doubles(int n, int nu, int ml) { return (size_t)ml * ml + (size_t)ml * (n + nu); }
 size_t riccati_sweep_ws_doubles(int n, int nu) { return 4 * (size_t)n * n + 2 * (size_t)nu * n; }
 
@@ -186,6 +191,9 @@ int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const do
     if (riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA"))      // K4: FP64 tensor-core sweep, P / Abar resident in shared memory
         return riccati_sweep_dmma_device(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws,
                                          (long long)riccati_sweep_ws_doubles(n, nu), stream);
+    if (n > 108 && riccati_big_eligible(n, nu) && !getenv("CCB_NO_DMMA"))   // K4b: blocked FP64 tensor-core GEMMs on the global workspace
+        return riccati_sweep_big_device(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws,
+                                        (long long)riccati_sweep_ws_doubles(n, nu), stream);
     riccati_sweep_kernel<<<S, RT, 0, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws);
     g_launches++;
     CCB_CUDA(cudaGetLastError());

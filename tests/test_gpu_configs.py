@@ -88,6 +88,20 @@ def test_c3_npendulum32_tree_solve(cc, orc):
     assert rel_err(A[0], ref["A"]) < TOL and rel_err(Bu[0], ref["Bu"]) < TOL and rel_err(Bl[0], ref["Bl"]) < TOL and rel_err(G[0], ref["G"]) < TOL
 
 
+def test_c3_npendulum16_gains_on_the_blocked_sweep(cc, orc):
+    """C3 beyond n = 108: the 16-link pendulum (n = 204) synthesises on K4b; short horizon so that the recursion is still well conditioned"""
+    mech, cfg = cc.examples.cartpole_n_pendulum(16)
+    om = orc.OracleMech(mech.desc())
+    eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    zd = zd_of(mech, cfg)
+    Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
+    out = cc.lqr_synthesize(mech, zd[None], np.zeros((1, 1)), eqc_idx, Qd, Rd, 30)
+    lin = om.linearize(zd, [0.0], eqc_idx)
+    ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd, Rd, 30)
+    assert out["kexit"][0] == ref["kexit"]
+    assert rel_err(out["Ku"][0], ref["Ku"]) < 1e-9
+
+
 # ------------------------------------------------------------------------------------------------ C4: Sawyer
 def sawyer_states(cc, mech, B, seed, amp):
     rng = np.random.default_rng(seed)

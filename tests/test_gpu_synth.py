@@ -50,6 +50,22 @@ def test_dlqr_matches_oracle_random_and_unconstrained(cc, orc):
         assert rel_err(out["Ku"][s], ref["Ku"]) < TOL
 
 
+@pytest.mark.parametrize("n,nu,ml,N", [(132, 3, 20, 25), (204, 1, 85, 12), (116, 8, 0, 20)])
+def test_dlqr_large_state_blocked_tensor_core_sweep(cc, orc, n, nu, ml, N):
+    """n > 108 runs on K4b (P, Abar in the global workspace, blocked DMMA products): same gains and exit index as the oracle"""
+    rng = np.random.default_rng(n)
+    S = 3
+    A = rng.normal(size=(S, n, n)) * (0.9 / np.sqrt(n))
+    Bu = rng.normal(size=(S, n, nu)); G = rng.normal(size=(S, ml, n))
+    Bl = np.swapaxes(G, 1, 2) + 0.1 * rng.normal(size=(S, n, ml))          # G Bl ~ G G': a well conditioned projection
+    L = rng.normal(size=(n, n)); Q = (L @ L.T / n + np.eye(n)) * 0.01; R = np.eye(nu) * 0.02
+    out = cc.dlqr(A, Bu, Bl, G, Q, R, N)
+    for s in range(S):
+        ref = orc.dlqr(A[s], Bu[s], Bl[s], G[s], Q, R, N)
+        assert out["kexit"][s] == ref["kexit"] and out["iters"][s] == ref["iters"]
+        assert rel_err(out["Ku"][s], ref["Ku"]) < TOL
+
+
 def test_lqr_pendulum_reference_example(cc, orc):
     # examples/lqr_pendulum.jl end to end through the reference API: LQR(...) then simulate!(mech, 10, lqr, record=true)
     mech, cfg = cc.examples.pendulum()

@@ -17,7 +17,7 @@ def main():
     zd = zd_of(mech, cfg)
     Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
     lin = om.linearize(zd, [0.0], eqc_idx)
-    for N in (2, 5, 20, 80, 300):
+    for N in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (2, 5, 20, 80, 300)):
         out = cc.lqr_synthesize(mech, zd[None], np.zeros((1, 1)), eqc_idx, Qd, Rd, N)
         ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd, Rd, N)
         e = np.abs(out["Ku"][0] - ref["Ku"]).max() / np.abs(ref["Ku"]).max()
