@@ -8,9 +8,10 @@
 // cover n with the least padding: 4 x 104 for n = 396, 2 x 104 for n = 204), warp w owns the 8-row strip w of the block, and
 // 16-deep k-panels of both operands are staged through shared memory (register-prefetched, double buffered, one barrier
 // per panel).  Both products are of the form A' B with row-major A, B:  W = P'Abar because P is symmetric,  Abar'W as is;
-// so one panel layout serves both and every fragment load is conflict free (row length 136 = 8 mod 32).
+// so one panel layout serves both and every fragment load is conflict free (row length 132 = 4 mod 16).
 // P+ is symmetric: only blocks on or above the diagonal are formed and mirrored, and the diagonal blocks are averaged with
 // their transposes so that P stays exactly symmetric (for why that matters).
+#include <algorithm>
 #include <cstdlib>
 #include "ccb_dev_math.cuh"
 #include "ccb_internal.h"
@@ -22,7 +23,7 @@ namespace {
 constexpr int BT = 16;           // tiles per block edge (max) = warps per CTA (16 warps: 128 registers per thread)
 constexpr int NTB = BT * 32;     // threads per CTA
 constexpr int BK = 16;           // k-panel depth
-constexpr int PLD = 136;         // panel row length in shared memory: = 8 (mod 32), >= 8 BT
+constexpr int PLD = 132;         // panel row length in shared memory: = 4 (mod 16) so that a half-warp's fragment load touches 16 distinct banks; >= 8 BT
 constexpr int PANEL = BK * PLD;  // doubles per operand panel
 constexpr int NSLOT = (2 * PANEL / 2 + NTB - 1) / NTB;   // double2 slots per thread of one panel pair
 
@@ -33,8 +34,10 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // acc (+)= A' B restricted to rows i0 .. i0 + 8 tbm of A' (columns of A) and columns j0 .. j0 + 8 tbn of B.
 // A, B: [K][ld] row-major in global memory, valid columns < ncol.  sm: 4 * PANEL doubles.  All NTB threads call it.
 // On exit thread (warp w < tbm, g, t4) holds in acc[j] the elements (i0 + 8 w + g, j0 + 8 j + 2 t4 + {0, 1}).
-__device__ __forceinline__ void block_gemm_tn(int K, int ncol, const double* A, int lda, int i0, int tbm, const double* B, int ldb, int j0, int tbn,
-                                              double* sm, double (&acc)[BT][2]) {
+template <int TBN>
+__device__ __forceinline__ void block_gemm_tn_t(int K, int ncol, const double* A, int lda, int i0, int tbm, const double* B, int ldb, int j0,
+                                                double* sm, double (&acc)[BT][2]) {
+    constexpr int tbn = TBN;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
 #pragma unroll
     for (int j = 0; j < BT; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
@@ -74,9 +77,17 @@ __device__ __forceinline__ void block_gemm_tn(int K, int ncol, const double* A, 
             for (int kk = 0; kk < BK; kk += 4) {
                 const double a = As[(kk + t4) * PLD];
                 const double* br = Bs + (kk + t4) * PLD;
+                // fragment loads in groups of (up to) 8 ahead of their DMMAs: the load latency overlaps instead of serialising
 #pragma unroll
-                for (int j = 0; j < BT; j++)
-                    if (j < tbn) dmma(acc[j][0], acc[j][1], a, br[8 * j]);
+                for (int j0g = 0; j0g < TBN; j0g += 8) {
+                    double b[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (j0g + j < TBN) b[j] = br[8 * (j0g + j)];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (j0g + j < TBN) dmma(acc[j0g + j][0], acc[j0g + j][1], a, b[j]);
+                }
             }
         }
         if (p + 1 < np) store((p + 1) & 1);
@@ -85,6 +96,7 @@ __device__ __forceinline__ void block_gemm_tn(int K, int ncol, const double* A, 
 }
 
 // workspace per system: P, P1, Abar, W (4 n^2).  Dynamic shared memory: 4 PANEL + 3 nu n doubles.
+template <int TB>
 __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu, int N, const double* __restrict__ At, const double* __restrict__ D,
                                                                     long long stride_t_A, long long stride_t_D, long long stride_s_A, long long stride_s_D,
                                                                     const double* __restrict__ Q, long long Q_bs, const double* __restrict__ R, long long R_bs,
@@ -107,7 +119,8 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
     const double* Qs = Q + s * Q_bs;
     const double* Rg = R + s * R_bs;
     double* Kout = Ku + s * (size_t)(N - 1) * nu * n;
-    const int T = (n + 7) / 8, nblk = (T + BT - 1) / BT, tb = (T + nblk - 1) / nblk;      // blocks of tb x tb tiles
+    constexpr int tb = TB;                                                                  // blocks of TB x TB tiles (the last one zero padded)
+    const int T = (n + 7) / 8, nblk = (T + tb - 1) / tb;
 
     for (size_t t = tid; t < nn; t += NTB) P[t] = Qs[t];             // lqr.jl:147  Pk = Q
     for (int t = tid; t < nu * nu; t += NTB) Rs[t] = Rg[t];
@@ -123,6 +136,7 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
             double a[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) a[q] = 0.0;
+#pragma unroll 8
             for (int r = 0; r < n; r++) {
                 const double p = P[(size_t)r * n + j];
 #pragma unroll
@@ -145,6 +159,7 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
             double a[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) a[q] = 0.0;
+#pragma unroll 8
             for (int r = 0; r < n; r++) {
                 const double av = Ak[(size_t)r * n + j];
 #pragma unroll
@@ -187,72 +202,78 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
         }
         __syncthreads();
         // ---- Abar = Ã - D Ku                                                                        lqr.jl:169
-        for (size_t t = tid; t < nn; t += NTB) {
-            const int i = (int)(t / n), j = (int)(t % n);
-            double acc = Ak[t];
-            for (int q = 0; q < nu; q++) acc = fma(-Dk[(size_t)i * nu + q], Kk[(size_t)q * n + j], acc);
-            Abar[t] = acc;
+        for (int i = w; i < n; i += BT) {                             // a row per warp: coalesced, no integer divisions
+            double dq[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) dq[q] = q < nu ? -Dk[(size_t)i * nu + q] : 0.0;
+            for (int j = lane; j < n; j += 32) {
+                double acc = Ak[(size_t)i * n + j];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (q < nu) acc = fma(dq[q], Kk[(size_t)q * n + j], acc);
+                Abar[(size_t)i * n + j] = acc;
+            }
         }
         __syncthreads();
         // ---- W = P Abar = P' Abar
         for (int bi = 0; bi < nblk; bi++)
             for (int bj = 0; bj < nblk; bj++) {
-                const int ti0 = bi * tb, tj0 = bj * tb, tbm = min(tb, T - ti0), tbn = min(tb, T - tj0);
+                const int ti0 = bi * tb, tj0 = bj * tb, tbm = min(tb, T - ti0);
                 double acc[BT][2];
-                block_gemm_tn(n, n, P, n, 8 * ti0, tbm, Abar, n, 8 * tj0, tbn, panels, acc);
+                block_gemm_tn_t<TB>(n, n, P, n, 8 * ti0, tbm, Abar, n, 8 * tj0, panels, acc);
                 const int i = 8 * (ti0 + w) + g;
                 if (w < tbm && i < n) {
 #pragma unroll
-                    for (int j = 0; j < BT; j++) {
+                    for (int j = 0; j < TB; j++) {
                         const int c = 8 * (tj0 + j) + 2 * t4;
-                        if (j < tbn && c < n) *reinterpret_cast<double2*>(W + (size_t)i * n + c) = make_double2(acc[j][0], acc[j][1]);
+                        if (c < n) *reinterpret_cast<double2*>(W + (size_t)i * n + c) = make_double2(acc[j][0], acc[j][1]);
                     }
                 }
             }
         __syncthreads();
         // ---- P+ = Q + Abar' W + Ku' R Ku : blocks on and above the diagonal, mirrored                lqr.jl:170
+        double nd = 0.0;
         for (int bi = 0; bi < nblk; bi++)
             for (int bj = bi; bj < nblk; bj++) {
-                const int ti0 = bi * tb, tj0 = bj * tb, tbm = min(tb, T - ti0), tbn = min(tb, T - tj0);
+                const int ti0 = bi * tb, tj0 = bj * tb, tbm = min(tb, T - ti0);
                 double acc[BT][2];
-                block_gemm_tn(n, n, Abar, n, 8 * ti0, tbm, W, n, 8 * tj0, tbn, panels, acc);
+                block_gemm_tn_t<TB>(n, n, Abar, n, 8 * ti0, tbm, W, n, 8 * tj0, panels, acc);
                 const int i = 8 * (ti0 + w) + g;
-                if (w < tbm && i < n) {
+                if (w < tbm) {                                   // warp-uniform: the shuffles below need the whole warp
+                    const bool iok = i < n;
                     double ki[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) ki[q] = q < nu ? Kk[(size_t)q * n + i] : 0.0;
+                    for (int q = 0; q < 8; q++) ki[q] = (q < nu && iok) ? Kk[(size_t)q * n + i] : 0.0;
 #pragma unroll
-                    for (int j = 0; j < BT; j++) {
+                    for (int j = 0; j < TB; j++) {
                         const int c = 8 * (tj0 + j) + 2 * t4;
-                        if (j < tbn && c < n) {
+                        const bool ok = iok && c < n;
+                        double v0 = acc[j][0], v1 = acc[j][1];
+                        if (ok) {
                             const double2 qv = *reinterpret_cast<const double2*>(Qs + (size_t)i * n + c);
-                            double v0 = acc[j][0] + qv.x, v1 = acc[j][1] + qv.y;
+                            v0 += qv.x; v1 += qv.y;
 #pragma unroll
                             for (int q = 0; q < 8; q++)
                                 if (q < nu) { v0 = fma(ki[q], RK[(size_t)q * n + c], v0); v1 = fma(ki[q], RK[(size_t)q * n + c + 1], v1); }
-                            *reinterpret_cast<double2*>(P1 + (size_t)i * n + c) = make_double2(v0, v1);
-                            if (bj > bi) { P1[(size_t)c * n + i] = v0; P1[(size_t)(c + 1) * n + i] = v1; }
                         }
+                        if (bj == bi && j == w) {      // diagonal tile: average with its own transpose (exact symmetry)
+                            const int src0 = (2 * t4) * 4 + (g >> 1), src1 = (2 * t4 + 1) * 4 + (g >> 1);
+                            const double u00 = __shfl_sync(0xffffffffu, v0, src0), u01 = __shfl_sync(0xffffffffu, v1, src0);
+                            const double u10 = __shfl_sync(0xffffffffu, v0, src1), u11 = __shfl_sync(0xffffffffu, v1, src1);
+                            v0 = 0.5 * (v0 + ((g & 1) ? u01 : u00));
+                            v1 = 0.5 * (v1 + ((g & 1) ? u11 : u10));
+                        }
+                        if (ok && (bj > bi || j >= w)) {
+                            *reinterpret_cast<double2*>(P1 + (size_t)i * n + c) = make_double2(v0, v1);
+                            const double2 po = *reinterpret_cast<const double2*>(P + (size_t)i * n + c);       // ‖P - P+‖_F^2: a mirrored tile counts twice
+                            const double d0 = po.x - v0, d1 = po.y - v1, wgt = (bj > bi || j > w) ? 2.0 : 1.0;
+                            nd = fma(wgt * d0, d0, nd); nd = fma(wgt * d1, d1, nd);
+                        }
+                        if (ok && (bj > bi || j > w)) { P1[(size_t)c * n + i] = v0; P1[(size_t)(c + 1) * n + i] = v1; }
                     }
                 }
             }
         __syncthreads();
-        // diagonal blocks: average with the transpose (each unordered pair owned by one thread)
-        for (int b = 0; b < nblk; b++) {
-            const int o = 8 * b * tb, m = min(8 * tb, n - o);
-            for (int e = tid; e < m * m; e += NTB) {
-                const int i = e / m, j = e % m;
-                if (i < j) {
-                    double* pa = P1 + (size_t)(o + i) * n + o + j;
-                    double* pb = P1 + (size_t)(o + j) * n + o + i;
-                    const double v = 0.5 * (*pa + *pb);
-                    *pa = v; *pb = v;
-                }
-            }
-        }
-        __syncthreads();
-        double nd = 0.0;                                                                             // ‖P - P+‖_F
-        for (size_t t = tid; t < nn; t += NTB) { const double d = P[t] - P1[t]; nd = fma(d, d, nd); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
         if (lane == 0) red[w] = nd;
@@ -285,9 +306,18 @@ int riccati_sweep_big_device(int S, int n, int nu, int N, const double* At, cons
                              long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
     const size_t smem = (4 * (size_t)PANEL + 3 * (size_t)nu * n) * sizeof(double);
-    CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    riccati_sweep_big_kernel<<<S, NTB, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters,
-                                                       ws, ws_stride);
+    const int T = (n + 7) / 8, nblk = (T + BT - 1) / BT, tb = std::max(8, (T + nblk - 1) / nblk);     // least padding with blocks of at most BT tiles
+    switch (tb) {
+#define CCB_BIG(TB_)                                                                                                                              \
+    case TB_:                                                                                                                                     \
+        CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_big_kernel<TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        riccati_sweep_big_kernel<TB_><<<S, NTB, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, \
+                                                                Ku, kexit, iters, ws, ws_stride);                                                 \
+        break;
+        CCB_BIG(8) CCB_BIG(9) CCB_BIG(10) CCB_BIG(11) CCB_BIG(12) CCB_BIG(13) CCB_BIG(14) CCB_BIG(15) CCB_BIG(16)
+#undef CCB_BIG
+        default: set_error("riccati (blocked): unsupported block shape"); return CCB_E_UNSUPPORTED;
+    }
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;
