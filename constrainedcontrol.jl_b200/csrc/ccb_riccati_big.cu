@@ -6,8 +6,7 @@
 // One CTA of 16 warps per system; P, P+, Abar, W live in a global workspace (L2 / HBM) and the two n^3 products are blocked
 // FP64 tensor-core GEMMs: the output is cut into square blocks of tb x tb 8x8 tiles (tb <= 16, chosen so that the blocks
 // cover n with the least padding: 4 x 104 for n = 396, 2 x 104 for n = 204), warp w owns the 8-row strip w of the block, and
-// 16-deep k-panels of both operands are staged through shared memory (register-prefetched, double buffered, one barrier
-// per panel).  Both products are of the form A' B with row-major A, B:  W = P'Abar because P is symmetric,  Abar'W as is;
+// 16-deep k-panels of both operands are staged through shared memory (cp.async, four stages in flight, one barrier per panel).  Both products are of the form A' B with row-major A, B:  W = P'Abar because P is symmetric,  Abar'W as is;
 // so one panel layout serves both and every fragment load is conflict free (row length 132 = 4 mod 16).
 // P+ is symmetric: only blocks on or above the diagonal are formed and mirrored, and the diagonal blocks are averaged with
 // their transposes so that P stays exactly symmetric (for why that matters).
@@ -25,15 +24,23 @@ constexpr int NTB = BT * 32;     // threads per CTA
 constexpr int BK = 16;           // k-panel depth
 constexpr int PLD = 132;         // panel row length in shared memory: = 4 (mod 16) so that a half-warp's fragment load touches 16 distinct banks; >= 8 BT
 constexpr int PANEL = BK * PLD;  // doubles per operand panel
-constexpr int NSLOT = (2 * PANEL / 2 + NTB - 1) / NTB;   // double2 slots per thread of one panel pair
+constexpr int NSLOT = (2 * PANEL / 2 + NTB - 1) / NTB;   // 16-byte pieces per thread of one panel pair
+constexpr int NST = 4;           // panel pairs in flight (cp.async stages)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // acc (+)= A' B restricted to rows i0 .. i0 + 8 tbm of A' (columns of A) and columns j0 .. j0 + 8 tbn of B.
-// A, B: [K][ld] row-major in global memory, valid columns < ncol.  sm: 4 * PANEL doubles.  All NTB threads call it.
+// A, B: [K][ld] row-major in global memory, valid columns < ncol.  sm: 2 NST PANEL doubles.  All NTB threads call it.
 // On exit thread (warp w < tbm, g, t4) holds in acc[j] the elements (i0 + 8 w + g, j0 + 8 j + 2 t4 + {0, 1}).
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int src_bytes) {      // src_bytes 0: zero fill
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 template <int TBN>
 __device__ __forceinline__ void block_gemm_tn_t(int K, int ncol, const double* A, int lda, int i0, int tbm, const double* B, int ldb, int j0,
                                                 double* sm, double (&acc)[BT][2]) {
@@ -42,37 +49,35 @@ __device__ __forceinline__ void block_gemm_tn_t(int K, int ncol, const double* A
 #pragma unroll
     for (int j = 0; j < BT; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
     const int np = (K + BK - 1) / BK;
-    // my four double2 slots of a panel pair: e = tid + q * NTB -> operand, row, column pair
-    double2 pre[NSLOT];
-    auto load = [&](int p) {
+    // a panel pair is PANEL 16-byte pieces [op][row][column pair]; thread t copies pieces t, t + NTB, ... straight into shared memory
+    // (cp.async, zero fill outside the matrix): NST stages in flight hide the HBM latency behind NST - 1 panels of DMMAs
+    auto issue = [&](int p) {
+        if (p < np) {
+            double* dst = sm + (size_t)(p % NST) * 2 * PANEL;
 #pragma unroll
-        for (int q = 0; q < NSLOT; q++) {
-            const int e = tid + q * NTB;
-            if (e >= PANEL) { pre[q] = make_double2(0.0, 0.0); continue; }
-            const int op = e / (BK * (PLD / 2)), rem = e % (BK * (PLD / 2)), row = rem / (PLD / 2), col = 2 * (rem % (PLD / 2));
-            const int kk = p * BK + row;
-            const int x = (op ? j0 : i0) + col;
-            const bool ok = kk < K && x < ncol && col < 8 * (op ? tbn : tbm);
-            double2 v = make_double2(0.0, 0.0);
-            if (ok) v = *reinterpret_cast<const double2*>((op ? B : A) + (size_t)kk * (op ? ldb : lda) + x);
-            pre[q] = v;
+            for (int q = 0; q < NSLOT; q++) {
+                const int e = tid + q * NTB;
+                if (e < PANEL) {
+                    const int op = e / (BK * (PLD / 2)), rem = e % (BK * (PLD / 2)), row = rem / (PLD / 2), col = 2 * (rem % (PLD / 2));
+                    const int kk = p * BK + row;
+                    const int x = (op ? j0 : i0) + col;
+                    const bool ok = kk < K && x < ncol && col < 8 * (op ? tbn : tbm);
+                    const double* src = ok ? (op ? B : A) + (size_t)kk * (op ? ldb : lda) + x : A;
+                    cp_async16(dst + 2 * e, src, ok ? 16 : 0);
+                }
+            }
         }
+        cp_async_commit();
     };
-    auto store = [&](int buf) {
 #pragma unroll
-        for (int q = 0; q < NSLOT; q++) {
-            const int e = tid + q * NTB;
-            if (e < PANEL) *reinterpret_cast<double2*>(sm + (size_t)buf * 2 * PANEL + 2 * e) = pre[q];      // [op][row][col]: e enumerates it in order
-        }
-    };
-    load(0);
-    store(0);
-    __syncthreads();
+    for (int p = 0; p < NST - 1; p++) issue(p);
     for (int p = 0; p < np; p++) {
-        if (p + 1 < np) load(p + 1);
+        cp_async_wait<NST - 2>();          // my pieces of panel p have landed
+        __syncthreads();                   // ... and everybody else's; stage (p - 1) % NST is free again
+        issue(p + NST - 1);
         if (w < tbm) {
-            const double* As = sm + (size_t)(p & 1) * 2 * PANEL + 8 * w + g;
-            const double* Bs = sm + (size_t)(p & 1) * 2 * PANEL + PANEL + g;
+            const double* As = sm + (size_t)(p % NST) * 2 * PANEL + 8 * w + g;
+            const double* Bs = sm + (size_t)(p % NST) * 2 * PANEL + PANEL + g;
 #pragma unroll
             for (int kk = 0; kk < BK; kk += 4) {
                 const double a = As[(kk + t4) * PLD];
@@ -90,9 +95,9 @@ __device__ __forceinline__ void block_gemm_tn_t(int K, int ncol, const double* A
                 }
             }
         }
-        if (p + 1 < np) store((p + 1) & 1);
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();                       // the stages may be refilled by the next block
 }
 
 // workspace per system: P, P1, Abar, W (4 n^2).  Dynamic shared memory: 4 PANEL + 3 nu n doubles.
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
     const size_t s = blockIdx.x, nn = (size_t)n * n;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     double* panels = big_sm;
-    double* DtP = big_sm + 4 * PANEL;            // [nu][n]  (later R Ku)
+    double* DtP = big_sm + 2 * NST * PANEL;            // [nu][n]  (later R Ku)
     double* Kk = DtP + (size_t)nu * n;           // [nu][n]
     double* RK = Kk + (size_t)nu * n;            // [nu][n]
     double* P = ws + s * ws_stride;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
             double dq[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) dq[q] = q < nu ? -Dk[(size_t)i * nu + q] : 0.0;
+#pragma unroll 4
             for (int j = lane; j < n; j += 32) {
                 double acc = Ak[(size_t)i * n + j];
 #pragma unroll
@@ -299,13 +305,13 @@ __global__ void __launch_bounds__(NTB, 1) riccati_sweep_big_kernel(int n, int nu
 
 // n even (it is 12 nb), nu <= 8; the nu x n operands must fit next to the panels
 bool riccati_big_eligible(int n, int nu) {
-    return n % 2 == 0 && nu >= 1 && nu <= 8 && (4 * (size_t)PANEL + 3 * (size_t)nu * n) * sizeof(double) <= 220 * 1024;
+    return n % 2 == 0 && nu >= 1 && nu <= 8 && (2 * (size_t)NST * PANEL + 3 * (size_t)nu * n) * sizeof(double) <= 225 * 1024;
 }
 
 int riccati_sweep_big_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                              long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
-    const size_t smem = (4 * (size_t)PANEL + 3 * (size_t)nu * n) * sizeof(double);
+    const size_t smem = (2 * (size_t)NST * PANEL + 3 * (size_t)nu * n) * sizeof(double);
     const int T = (n + 7) / 8, nblk = (T + BT - 1) / BT, tb = std::max(8, (T + nblk - 1) / nblk);     // least padding with blocks of at most BT tiles
     switch (tb) {
 #define CCB_BIG(TB_)                                                                                                                              \
