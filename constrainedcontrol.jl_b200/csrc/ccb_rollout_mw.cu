@@ -48,8 +48,8 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
     double* xM = xd + nj * 6;                   // [nj][9]    Tw D^-1 of the body
     double* xl = xM + nj * 9;                   // [5 nj + 5] multipliers / substitution results per row (+5: reads past the leaf)
     double* xf = xl + 5 * nj + 5;               // [nj][6]    force sums
-    double* pivb = xf + nj * 6;                 // [2][12]    pivot row, double buffered
-    double* red = pivb + 24;                    // [5 nj]     per-row partials
+    double* pivb = xf + nj * 6;                 // [2][2][12] pivot rows of the two elimination streams, double buffered
+    double* red = pivb + 48;                    // [5 nj]     per-row partials
     double* red2 = red + 5 * nj;                // [nj]       per-joint partials
     double* xu = red2 + nj;                     // [nj + 1]   joint inputs
     double* ured = xu + nj + 1;                 // [8][5 nj]  control-law partials (up to 8 inputs per round)
@@ -438,51 +438,104 @@ __global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const
         };
 
         double dl = 0.0, ds[6];
+        // S dλ = rhs, one row per lane, block tridiagonal along the chain.  Two-sided ("twisted") elimination: the blocks below the
+        // middle block mid = nj / 2 are eliminated from the leaf inwards and, in the same rounds, the blocks above it from the root
+        // inwards (the two pivot streams touch disjoint rows except for the middle block, which takes both updates); then the middle
+        // block; then the substitution runs outwards from the middle in both directions at once.  5 (max(mid, nj-1-mid) + 1) pivot
+        // rounds instead of 5 nj.  Inside a block the elimination is Gauss-Jordan, so a block's rows end up diagonal in their own block.
+        // Lanes above the middle swap their parent / child couplings, so that for every lane rowP is the coupling TOWARDS the middle
+        // (still to be eliminated against) and rowC the coupling AWAY from it, and one update code serves both streams.
         auto solve = [&]() {
             double myinv = 1.0;
             int par = 0;
+            const int mid = nj >> 1, nst_blocks = max(mid, nj - 1 - mid);
+            const bool top = lane_ok && pos < mid, ismid = lane_ok && pos == mid;
+            if (top) {
+#pragma unroll
+                for (int c = 0; c < 5; c++) { const double t = rowP[c]; rowP[c] = rowC[c]; rowC[c] = t; }
+            }
             const int wlo = (q >> 5) << 5, whi = wlo + 31;     // rows held by my warp
-            const bool many_warps = true;
-            for (int pp = nj - 1; pp >= 0; pp--) {
+            const bool warp_has_mid = !(wlo > 5 * mid + 4 || whi < 5 * mid);
+            for (int sb = 0; sb < nst_blocks; sb++) {
+                const int ppb = nj - 1 - sb, ppt = sb;           // pivot blocks of the two streams
+                const bool vb = ppb > mid, vt = ppt < mid;
+                const int ppv = top ? ppt : ppb;                 // the pivot block that can concern me, and its neighbour towards the middle
+                const int nbv = top ? ppt + 1 : ppb - 1;
+                const bool vv = top ? vt : vb;
 #pragma unroll
                 for (int rk = 4; rk >= 0; rk--) {
-                    double* buf = pivb + 12 * par;
+                    double* bufB = pivb + 24 * par;
+                    double* bufT = bufB + 12;
                     par ^= 1;
-                    if (lane_ok && pos == pp && r == rk) {       // publish my row: own-block entries left of the pivot, parent block, rhs, pivot
+                    if (lane_ok && vv && pos == ppv && r == rk) {       // publish my row: own block, coupling towards the middle, rhs, pivot
+                        double* buf = top ? bufT : bufB;
 #pragma unroll
                         for (int c = 0; c < 5; c++) { buf[c] = rowO[c]; buf[5 + c] = rowP[c]; }
                         buf[10] = rhs; buf[11] = rowO[rk];
                     }
                     __syncthreads();
-                    // only the warps holding rows of the pivot's block or of its parent block have anything to update
-                    if (many_warps && (wlo > 5 * pp + 4 || whi < 5 * (pp - 1))) continue;
-                    const double inv = rcp_nr(buf[11]);
-                    const bool mine = lane_ok && pos == pp && r == rk;
-                    if (mine) myinv = inv;
-                    const bool same = lane_ok && pos == pp && r != rk, parb = lane_ok && pos == pp - 1;
-                    const double fS = same ? rowO[rk] * inv : 0.0;
-                    const double fP = parb ? rowC[rk] * inv : 0.0;
+                    // only the warps holding rows of a pivot block or of its inner neighbour have anything to update
+                    const bool hitB = vb && !(wlo > 5 * ppb + 4 || whi < 5 * (ppb - 1));
+                    const bool hitT = vt && !(wlo > 5 * (ppt + 1) + 4 || whi < 5 * ppt);
+                    if (!hitB && !hitT) continue;
+                    {
+                        const double* buf = top ? bufT : bufB;
+                        const double inv = rcp_nr(vv ? buf[11] : 1.0);
+                        if (lane_ok && vv && pos == ppv && r == rk) myinv = inv;
+                        const bool same = lane_ok && vv && pos == ppv && r != rk, nbr = lane_ok && vv && pos == nbv;
+                        const double fS = same ? rowO[rk] * inv : 0.0;
+                        const double fN = nbr ? rowC[rk] * inv : 0.0;
 #pragma unroll
-                    for (int c = 0; c < rk; c++) {
-                        const double pv = buf[c];
-                        rowO[c] = fma(-fS, pv, rowO[c]);
-                        rowC[c] = fma(-fP, pv, rowC[c]);
-                    }
+                        for (int c = 0; c < rk; c++) {
+                            const double pv = buf[c];
+                            rowO[c] = fma(-fS, pv, rowO[c]);
+                            rowC[c] = fma(-fN, pv, rowC[c]);
+                        }
 #pragma unroll
-                    for (int c = 0; c < 5; c++) {
-                        const double pv = buf[5 + c];
-                        rowP[c] = fma(-fS, pv, rowP[c]);
-                        rowO[c] = fma(-fP, pv, rowO[c]);
+                        for (int c = 0; c < 5; c++) {
+                            const double pv = buf[5 + c];
+                            rowP[c] = fma(-fS, pv, rowP[c]);
+                            rowO[c] = fma(-fN, pv, rowO[c]);
+                        }
+                        rhs = fma(-(fS + fN), buf[10], rhs);
                     }
-                    rhs = fma(-(fS + fP), buf[10], rhs);
+                    // the middle block is the inner neighbour of the root-side stream as well: its coupling to block mid - 1 is rowP
+                    if (warp_has_mid && vt && ppt + 1 == mid) {
+                        const double inv = rcp_nr(bufT[11]);
+                        const double fN = ismid ? rowP[rk] * inv : 0.0;
+#pragma unroll
+                        for (int c = 0; c < rk; c++) rowP[c] = fma(-fN, bufT[c], rowP[c]);
+#pragma unroll
+                        for (int c = 0; c < 5; c++) rowO[c] = fma(-fN, bufT[5 + c], rowO[c]);
+                        rhs = fma(-fN, bufT[10], rhs);
+                    }
                 }
             }
-            // substitution root -> leaf, one joint per round: x = (rhs - P x_parent) / pivot
-            for (int pp = 0; pp < nj; pp++) {
-                if (lane_ok && pos == pp) {
+            // the middle block (nothing outside it is updated: its neighbours are already eliminated)
+#pragma unroll
+            for (int rk = 4; rk >= 0; rk--) {
+                double* buf = pivb + 24 * par;
+                par ^= 1;
+                if (ismid && r == rk) {
+#pragma unroll
+                    for (int c = 0; c < 5; c++) buf[c] = rowO[c];
+                    buf[10] = rhs; buf[11] = rowO[rk];
+                }
+                __syncthreads();
+                if (!warp_has_mid) continue;
+                const double inv = rcp_nr(buf[11]);
+                if (ismid && r == rk) myinv = inv;
+                const double fS = (ismid && r != rk) ? rowO[rk] * inv : 0.0;
+#pragma unroll
+                for (int c = 0; c < rk; c++) rowO[c] = fma(-fS, buf[c], rowO[c]);
+                rhs = fma(-fS, buf[10], rhs);
+            }
+            // substitution outwards from the middle, one block of each side per round: x = (rhs - (coupling towards the middle) x_inner) / pivot
+            for (int j = 0; j <= nst_blocks; j++) {
+                if (lane_ok && ((j == 0 && ismid) || (j > 0 && (pos == mid - j || pos == mid + j)))) {
                     double x = rhs;
-                    if (pp > 0) {
-                        const double* xp = xl + 5 * (pp - 1);
+                    if (j > 0) {
+                        const double* xp = xl + 5 * (top ? pos + 1 : pos - 1);
 #pragma unroll
                         for (int c = 0; c < 5; c++) x = fma(-rowP[c], xp[c], x);
                     }
@@ -577,7 +630,7 @@ bool mw_kernel_eligible(const DevMech& M) {
 int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream) {
     const int nj = M.nj;
     const int threads = ((5 * nj + 31) / 32) * 32;
-    const size_t doubles = (size_t)nj * kGS + (size_t)nj * kCS + (size_t)nj * 8 + (size_t)nj * 6 + (size_t)nj * 9 + (5 * nj + 5) + (size_t)nj * 6 + 24 +
+    const size_t doubles = (size_t)nj * kGS + (size_t)nj * kCS + (size_t)nj * 8 + (size_t)nj * 6 + (size_t)nj * 9 + (5 * nj + 5) + (size_t)nj * 6 + 48 +
                            5 * nj + nj + (nj + 1) + 40 * nj + 8 * nj;
     const size_t smem = doubles * sizeof(double) + (size_t)nj * sizeof(int) + 16;
     if (smem > 227 * 1024) { set_error("mechanism too large for the multi-warp rows kernel"); return CCB_E_UNSUPPORTED; }
