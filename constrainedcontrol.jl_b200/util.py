@@ -24,8 +24,8 @@ def _batched(A, B, Q, R):
     if B.ndim == 1:
         B = B.reshape(n, 1)
     m = B.shape[-1]
-    if R.ndim == 0:
-        R = R.reshape(1, 1)
+    if R.ndim < 2:                  # a scalar weight (or one scalar per problem) for a single input
+        R = R.reshape(1, 1) if R.size == 1 else R.reshape(-1, 1, 1)
     single = A.ndim == 2 and B.ndim == 2 and Q.ndim == 2 and R.ndim == 2
     S = max(x.shape[0] if x.ndim == 3 else 1 for x in (A, B, Q, R))
     def full(x, r, c):

@@ -68,3 +68,18 @@ def test_pid_constructor_scalar_form_and_asserts(cc):
     d, _ = cc.examples.deltabot()
     with pytest.raises(AssertionError, match="Only 1 DOF"):
         cc.PID(d, d.eqconstraints[2].id, 0.0)
+
+
+def test_are_util_batches_and_broadcasts_without_touching_the_device(cc):
+    """util._batched (the host half of dare/care/lqr/dlqr): shared matrices broadcast over the batch, single problems stay single"""
+    import numpy as np
+    A = np.arange(8.0).reshape(2, 2, 2); B = np.ones((2, 1)); Q = np.eye(2); R = 2.0
+    Ab, Bb, Qb, Rb, S, n, m, single = cc.util._batched(A, B, Q, np.asarray(R))
+    assert (S, n, m, single) == (2, 2, 1, False)
+    assert Ab.shape == (2, 2, 2) and Bb.shape == (2, 2, 1) and Qb.shape == (2, 2, 2) and Rb.shape == (2, 1, 1)
+    assert Bb.flags.c_contiguous and np.array_equal(Bb[1], B) and Rb[1, 0, 0] == 2.0
+    _, _, _, _, S, n, m, single = cc.util._batched(A[0], B[:, 0], Q, [[2.0]])
+    assert (S, n, m, single) == (1, 2, 1, True)
+    import pytest
+    with pytest.raises(AssertionError):
+        cc.util._batched(A, np.ones((3, 2, 1)), Q, [[1.0]])      # batch sizes differ
