@@ -24,7 +24,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 __host__ __device__ inline int dmma_ld(int n) { return (n % 16 == 4 || n % 16 == 12) ? n : n + 4; }
 
 // NU1: scalar input (nu == 1): the nu x nu solve is a division and the generic elimination is compiled out (it costs ~128 registers).
-// STAGE (time-invariant problems): 2 = Ã, Q and the previous P also live in shared memory, so an iteration touches global memory only
+// STAGE: 3 = Ã in a third shared-memory matrix and the previous P of the tiles a warp forms in registers (72 <= n <= 84, time invariant);
+// (time-invariant problems) 2 = Ã, Q and the previous P also live in shared memory, so an iteration touches global memory only
 // to store the gain row (small n); 1 = the previous P is kept in a third shared-memory matrix instead of a global round trip (72 <= n <= 84:
 // three n x n matrices fit in 227 KB); 0 = Ã, Q stream from L2 and the previous P goes through the global copy.
 #ifndef K4_MINB_NUM
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                                                                      long long ws_stride) {
     extern __shared__ __align__(16) double sm[];
     constexpr int NT = 32 * T;
+    constexpr bool A_SM = STAGE >= 2, Q_SM = STAGE == 2, POLD_REG = STAGE >= 2;   // what a staged variant keeps on chip
     const int LD = dmma_ld(n);
     double* Ps = sm;                          // [n][LD]  P, then W = P Abar
     double* As = Ps + (size_t)n * LD;         // [n][LD]  Abar
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* Sc = Dp + (size_t)n * 8;          // [8][8]   R + D'P D
     double* Rs = Sc + 64;                     // [8][8]   R padded with an identity
     double* red = Rs + 64;                    // [T] partial sums (padded to 16)
-    double* Asm = red + 16;                   // STAGE == 2: [n][LD] Ã ; STAGE == 1: [n][LD] previous P
+    double* Asm = red + 16;                   // STAGE >= 2: [n][LD] Ã ; STAGE == 1: [n][LD] previous P
     double* Qsm = Asm + (STAGE ? (size_t)n * LD : 0);   // STAGE == 2: [n][LD] Q
     double* Pold = Qsm + (STAGE == 2 ? (size_t)n * LD : 0);  // (unused since the previous P of a staged problem is kept in registers)
     __shared__ int brk;
@@ -84,15 +86,15 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* ps_c = Ps + (size_t)ra * LD + 2 * t4;             // my C elements of tile column j are at [8 j], [8 j + 1]
     double* as_c = As + (size_t)ra * LD + 2 * t4;
     double* pg_c = Pg + (size_t)ra * n + 2 * t4;
-    const double* q_c = STAGE == 2 ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
+    const double* q_c = Q_SM ? Qsm + (size_t)ra * LD + 2 * t4 : Qs + (size_t)ra * n + 2 * t4;
     // previous P for the ‖P - P+‖ test: registers (STAGE 2), shared memory (STAGE 1: 72 <= n <= 84) or the global copy (STAGE 0)
     double* po_c = STAGE == 1 ? Asm + (size_t)ra * LD + 2 * t4 : pg_c;
     (void)Pold;
 
     for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
-    if (STAGE == 2) {
+    if (A_SM) {
         const double* A0 = At + s * stride_s_A;
-        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (STAGE == 2) Qsm[(size_t)i * LD + j] = Qs[e]; }
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (Q_SM) Qsm[(size_t)i * LD + j] = Qs[e]; }
     }
     for (int e = tid; e < 64; e += NT) { const int i = e >> 3, j = e & 7; Rs[e] = (i < nu && j < nu) ? Rg[i * nu + j] : (i == j ? 1.0 : 0.0); }
     for (int e = tid; e < NR * LD; e += NT) { DtP[e] = 0.0; Kk[e] = 0.0; RK[e] = 0.0; }
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 DtP[j] = (a0 + a1) + (a2 + a3);
             }
             __syncthreads();
-            const size_t lda = STAGE == 2 ? (size_t)LD : (size_t)n;
-            const double* Ab = STAGE == 2 ? Asm : Ak;
+            const size_t lda = A_SM ? (size_t)LD : (size_t)n;
+            const double* Ab = A_SM ? Asm : Ak;
             for (int j = tid; j < n; j += NT) {                       // (B) rhs[j] = sum_k DtP[k] Ã[k][j]
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 const double* ac = Ab + j;
@@ -162,8 +164,8 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             {
                 const int j0 = 8 * w, cb = min(j0 + g, n - 1);
                 double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-                const size_t lda = STAGE == 2 ? (size_t)LD : (size_t)n;
-                const double* ag = (STAGE == 2 ? Asm : Ak) + (size_t)t4 * lda + cb;
+                const size_t lda = A_SM ? (size_t)LD : (size_t)n;
+                const double* ag = (A_SM ? Asm : Ak) + (size_t)t4 * lda + cb;
                 const double* dr = DtP + g * LD + t4;
                 int k0 = 0;
                 for (; k0 + 16 <= n; k0 += 16) {                              // four independent loads in flight
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         // ---- (D) Abar = Ã - D Ku  (strip w; rank-8 update of Ã read from global in C layout)          lqr.jl:169
         double acc[T][2];
         {
-            const double* a_c = STAGE == 2 ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
+            const double* a_c = A_SM ? Asm + (size_t)ra * LD + 2 * t4 : Ak + (size_t)ra * n + 2 * t4;
 #pragma unroll
             for (int j = 0; j < T; j++) { acc[j][0] = ok0[j] ? a_c[8 * j] : 0.0; acc[j][1] = ok1[j] ? a_c[8 * j + 1] : 0.0; }
             if (NU1) {
@@ -272,14 +274,14 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             }
         }
         __syncthreads();
-        double pold[STAGE == 2 ? H : 1][2];
-        if constexpr (STAGE == 2) {                                      // small staged problems: previous P of my tiles stays in registers
+        double pold[POLD_REG ? H : 1][2];
+        if constexpr (POLD_REG) {                                      // small staged problems: previous P of my tiles stays in registers
 #pragma unroll
             for (int d = 0; d < H; d++) { pold[d][0] = ps_c[8 * jd[d]]; pold[d][1] = ps_c[8 * jd[d] + 1]; }
         }
 #pragma unroll
         for (int j = 0; j < T; j++) {                                    // old P -> shared / global copy (for the ‖P - P+‖ test), W -> shared
-            if constexpr (STAGE == 2) {
+            if constexpr (POLD_REG) {
                 if (ok0[j]) ps_c[8 * j] = acc[j][0];
                 if (ok1[j]) ps_c[8 * j + 1] = acc[j][1];
             } else {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
 #pragma unroll
         for (int d = 0; d < H; d++) {
             double p0, p1;
-            if constexpr (STAGE == 2) { p0 = pold[d][0]; p1 = pold[d][1]; }
+            if constexpr (POLD_REG) { p0 = pold[d][0]; p1 = pold[d][1]; }
             else { p0 = okd0[d] ? po_c[8 * jd[d]] : 0.0; p1 = okd1[d] ? po_c[8 * jd[d] + 1] : 0.0; }
             const double d0 = okd0[d] ? p0 - accF[d][0] : 0.0, d1 = okd1[d] ? p1 - accF[d][1] : 0.0;
             const double wgt = d == 0 ? 1.0 : 2.0;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
 
 size_t dmma_smem_bytes(int n, int T, int stage, bool nu1 = false) {
     const int LD = dmma_ld(n);
-    return ((size_t)(stage == 2 ? 4 : stage == 1 ? 3 : 2) * n * LD + 3 * (nu1 ? 1 : 8) * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
+    return ((size_t)(stage == 2 ? 4 : stage ? 3 : 2) * n * LD + 3 * (nu1 ? 1 : 8) * LD + (size_t)n * 8 + 128 + 16 + 8) * sizeof(double);
 }
 
 template <int T, bool NU1, int STAGE>
@@ -397,11 +399,13 @@ int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, con
                               int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
     const int T = (n + 7) / 8;
     const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
-    const bool stage_a = !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
+    const bool stage_a = !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;
+    const bool stage_b = stage_a && stride_t_A == 0;     // ... and, when Ã does not change, Ã in that third matrix with the previous P of my tiles in registers   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
 #define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream
 #define CCB_DMMA_CASE(TT)                                                                      \
     case TT:                                                                                   \
         if constexpr (TT <= 5) { if (stage) return nu == 1 ? launch_dmma<TT, true, 2>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 2>(CCB_DMMA_ARGS); } \
+        if constexpr (TT >= 9 && TT <= 11) { if (stage_b) return nu == 1 ? launch_dmma<TT, true, 3>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 3>(CCB_DMMA_ARGS); } \
         if constexpr (TT >= 9 && TT <= 11) { if (stage_a) return nu == 1 ? launch_dmma<TT, true, 1>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 1>(CCB_DMMA_ARGS); } \
         return nu == 1 ? launch_dmma<TT, true, 0>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 0>(CCB_DMMA_ARGS);
     switch (T) {
