@@ -13,6 +13,7 @@
 // Semantics identical to K1 / K1c / K1r: simulate! loop of ConstrainedDynamics.jl with the control
 // laws of reference src/control/lqr.jl:89-139, lqr_tracking.jl:46-71, pid.jl:43-88 fused.
 #include <algorithm>
+#include <cstdlib>
 #include "ccb_dev_math.cuh"
 #include "ccb_internal.h"
 
@@ -23,9 +24,6 @@ namespace {
 constexpr int kGS = 62;   // doubles per joint in the knot-row table: 5 rows x 12 (+2)
 constexpr int kCS = 24;   // constants per joint: p1 3, p2 3, qoff 4, axis 3, J 9, mass 1 (+1)
 
-#ifndef K1M_MAXREG
-#define K1M_MAXREG 255
-#endif
 
 __device__ __forceinline__ double rcp_nr(double x) {
     double y;
@@ -37,8 +35,11 @@ __device__ __forceinline__ double rcp_nr(double x) {
 }
 
 // NJT: number of joints as a compile-time constant (0 = run time): the shared-memory mailbox offsets fold into immediates
-template <int NJT>
-__global__ void __maxnreg__(K1M_MAXREG) rollout_mw_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const int* __restrict__ depth) {
+// MAXR: register cap of the variant.  The kernel is latency bound, so what matters is how the batch quantises into waves of resident
+// CTAs: 255 registers (no spills, 4 CTAs of 2 warps per SM) when the batch fits in one such wave or needs many, fewer registers (more
+// resident CTAs, some spills) when that turns two waves into one or lifts a long chain above ~8 warps per SM (launch_rollout_mw).
+template <int NJT, int MAXR>
+__global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const int* __restrict__ depth) {
     extern __shared__ __align__(16) double smem[];
     const int nj = NJT ? NJT : M.nj;
     double* gk = smem;                          // [nj][kGS]  knot rows: row t at t*12: GkA[6] | GkB[6]
@@ -634,18 +635,54 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
                            5 * nj + nj + (nj + 1) + 40 * nj + 8 * nj;
     const size_t smem = doubles * sizeof(double) + (size_t)nj * sizeof(int) + 16;
     if (smem > 227 * 1024) { set_error("mechanism too large for the multi-warp rows kernel"); return CCB_E_UNSUPPORTED; }
-#define CCB_MW_LAUNCH(NJT)                                                                                                    \
-    do {                                                                                                                     \
-        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        rollout_mw_kernel<NJT><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                                      \
+    int dev = 0, sms = 148;
+    CCB_CUDA(cudaGetDevice(&dev));
+    CCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static const int caps[3] = {255, 168, 128};
+    int occ[3] = {0, 0, 0};
+#define CCB_MW_OCC(NJT)                                                                                                               \
+    do {                                                                                                                             \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 255>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], rollout_mw_kernel<NJT, 255>, threads, smem));                \
+        CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], rollout_mw_kernel<NJT, 168>, threads, smem));                \
+        CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], rollout_mw_kernel<NJT, 128>, threads, smem));                \
+    } while (0)
+#define CCB_MW_LAUNCH(NJT)                                                                                                            \
+    do {                                                                                                                             \
+        if (pick == 0) rollout_mw_kernel<NJT, 255><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                          \
+        else if (pick == 1) rollout_mw_kernel<NJT, 168><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                     \
+        else rollout_mw_kernel<NJT, 128><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                                    \
     } while (0)
     switch (nj) {          // the BASELINE chain lengths get their own instantiation: Sawyer arm, 8-pendulum, 32-pendulum
+        case 7: CCB_MW_OCC(7); break;
+        case 9: CCB_MW_OCC(9); break;
+        case 33: CCB_MW_OCC(33); break;
+        default: CCB_MW_OCC(0); break;
+    }
+    // which register cap: one wave at 255 if the batch fits; else the largest cap that still makes ONE wave; else (many waves) the largest
+    // cap that keeps at least 8 warps per SM resident
+    int pick = -1;
+    const int wpc = threads / 32;
+    if ((long long)a.B <= (long long)sms * occ[0]) pick = 0;
+    for (int i = 1; i < 3 && pick < 0; i++)
+        if ((long long)a.B <= (long long)sms * occ[i]) pick = i;
+    for (int i = 0; i < 3 && pick < 0; i++)
+        if (occ[i] * wpc >= 8) pick = i;
+    if (pick < 0) pick = 2;
+    if (const char* e = getenv("CCB_K1M_REGS")) {      // experiments: force a variant
+        const int v = atoi(e);
+        for (int i = 0; i < 3; i++) if (caps[i] == v) pick = i;
+    }
+    switch (nj) {
         case 7: CCB_MW_LAUNCH(7); break;
         case 9: CCB_MW_LAUNCH(9); break;
         case 33: CCB_MW_LAUNCH(33); break;
         default: CCB_MW_LAUNCH(0); break;
     }
 #undef CCB_MW_LAUNCH
+#undef CCB_MW_OCC
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;
