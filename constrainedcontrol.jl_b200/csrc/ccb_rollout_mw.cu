@@ -14,6 +14,7 @@
 // laws of reference src/control/lqr.jl:89-139, lqr_tracking.jl:46-71, pid.jl:43-88 fused.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include "ccb_dev_math.cuh"
 #include "ccb_internal.h"
 
@@ -642,9 +643,9 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
     int occ[3] = {0, 0, 0};
 #define CCB_MW_OCC(NJT)                                                                                                               \
     do {                                                                                                                             \
-        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 255>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 255>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));        \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 168>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));         \
+        CCB_CUDA(cudaFuncSetAttribute(rollout_mw_kernel<NJT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));         \
         CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], rollout_mw_kernel<NJT, 255>, threads, smem));                \
         CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], rollout_mw_kernel<NJT, 168>, threads, smem));                \
         CCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], rollout_mw_kernel<NJT, 128>, threads, smem));                \
@@ -655,11 +656,28 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
         else if (pick == 1) rollout_mw_kernel<NJT, 168><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                     \
         else rollout_mw_kernel<NJT, 128><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                                    \
     } while (0)
-    switch (nj) {          // the BASELINE chain lengths get their own instantiation: Sawyer arm, 8-pendulum, 32-pendulum
-        case 7: CCB_MW_OCC(7); break;
-        case 9: CCB_MW_OCC(9); break;
-        case 33: CCB_MW_OCC(33); break;
-        default: CCB_MW_OCC(0); break;
+    // the attribute / occupancy queries are per (device, chain length, shared-memory size): remembered between launches
+    // (the shared-memory opt-in is raised to the device maximum once per variant, so a remembered entry never needs it again)
+    struct OccKey { int dev, nj; size_t smem; int occ[3]; };
+    static OccKey cache[8];
+    static int ncache = 0;
+    static std::mutex cache_mu;
+    std::lock_guard<std::mutex> lock(cache_mu);
+    int hit = -1;
+    for (int i = 0; i < ncache; i++)
+        if (cache[i].dev == dev && cache[i].nj == nj && cache[i].smem == smem) hit = i;
+    if (hit >= 0) {
+        for (int i = 0; i < 3; i++) occ[i] = cache[hit].occ[i];
+    } else {
+        switch (nj) {          // the BASELINE chain lengths get their own instantiation: Sawyer arm, 8-pendulum, 32-pendulum
+            case 7: CCB_MW_OCC(7); break;
+            case 9: CCB_MW_OCC(9); break;
+            case 33: CCB_MW_OCC(33); break;
+            default: CCB_MW_OCC(0); break;
+        }
+        OccKey& k = cache[ncache < 8 ? ncache++ : 7];
+        k.dev = dev; k.nj = nj; k.smem = smem;
+        for (int i = 0; i < 3; i++) k.occ[i] = occ[i];
     }
     // which register cap: one wave at 255 if the batch fits; else the largest cap that still makes ONE wave; else (many waves) the largest
     // cap that keeps at least 8 warps per SM resident
