@@ -41,7 +41,7 @@ def random_states(cc, mech, rng, B, amp=0.4, rate=0.5):
     return st
 
 
-@pytest.mark.parametrize("seed,nj", [(1, 1), (2, 2), (3, 3), (4, 4), (5, 6), (6, 7), (7, 9)])
+@pytest.mark.parametrize("seed,nj", [(1, 1), (2, 2), (3, 3), (4, 4), (8, 5), (5, 6), (6, 7), (7, 9), (9, 12)])
 def test_random_chain_rollout_every_kernel(cc, orc, seed, nj):
     rng = np.random.default_rng(seed)
     mech = random_chain(cc, rng, nj)
