@@ -437,8 +437,8 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         };
 
         // S dλ = rhs with one row per lane.  Elimination runs from the last row of the leaf joint to the first row of the
-        // root joint, so a pivot row only has entries to its left (parent block + own block) and the rows it updates are the
-        // earlier rows of its own block and the rows of the parent block: no fill.  On exit `rhs` holds dλ.
+        // root joint; a pivot row only has entries to its left (parent block + own block) and it updates the other rows of its own
+        // block (Gauss-Jordan: the block ends up diagonal) and the rows of the parent block: no fill.  On exit `rhs` holds dλ.
         auto solve = [&](double& xdl, double* xds) {
             __syncwarp();
             double myinv = 1.0;
@@ -451,9 +451,8 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
                     if (!lane_ok) piv = 1.0;
                     const double inv = rcp_fast(piv);
                     if (pos == pp && r == rk) myinv = inv;
-                    if (pp == 0 && rk == 0) break;                       // nothing left of the first row
-                    const bool same = (pos == pp) && (r < rk), par = (pos == pp - 1);
-                    const double fS = same ? rowO[rk] * inv : 0.0;       // factor when I am an earlier row of the pivot's block
+                    const bool same = (pos == pp) && (r != rk), par = (pos == pp - 1);
+                    const double fS = same ? rowO[rk] * inv : 0.0;       // factor when I am another row of the pivot's block (Gauss-Jordan inside the block)
                     const double fP = par ? rowC[rk] * inv : 0.0;        // factor when I am a row of the pivot's parent block
 #pragma unroll
                     for (int c = 0; c < rk; c++) {
@@ -473,17 +472,19 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
                     rhs = fma(-(fS + fP), pr_, rhs);
                 }
             }
-            // substitution, root row first: x_K = rhs_K / pivot_K, then it leaves the later rows of its block and the child block
+            // substitution, root joint first: the blocks are diagonal after the Gauss-Jordan sweeps, so a joint's five multipliers come
+            // out together: x = (rhs - (coupling to the parent block) x_parent) / pivot
 #pragma unroll
             for (int pp = 0; pp < NJ; pp++) {
+                double xs = rhs;
+                if (pp > 0) {
 #pragma unroll
-                for (int rk = 0; rk < 5; rk++) {
-                    const int src = base + 5 * pp + rk;
-                    const double xk = shfl_d(rhs * myinv, src);
-                    if (pos == pp && r == rk) rhs = xk;
-                    const double coef = (pos == pp && r > rk) ? rowO[rk] : ((pos == pp + 1) ? rowP[rk] : 0.0);
-                    rhs = fma(-coef, xk, rhs);
+                    for (int c = 0; c < 5; c++) {
+                        const double xpar = shfl_d(rhs, base + 5 * (pp - 1) + c);
+                        xs = fma(-rowP[c], xpar, xs);
+                    }
                 }
+                if (pos == pp) rhs = xs * myinv;
             }
             xdl = rhs;
             // body step ds = D^-1 (d + G_own,B^T dλ_own + G_child,A^T dλ_child)
