@@ -197,6 +197,7 @@ def tracking_bench(cc, torch, dev):
         tl = cc.TrackingLQR(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"], device=dev)
         synth_wall = time.time() - t0
     ph = cc.synth.phase_ms()
+    dev_ms = cc.synth.phase_total_ms()       # the phases overlap (linearisation + projection of the next block of steps behind the sweep)
     B = NT * PER
     stp = np.repeat(st0, PER, axis=0)
     for s_ in range(B):
@@ -217,8 +218,8 @@ def tracking_bench(cc, torch, dev):
     fin = batch.get_state()
     err = float(np.abs(fin[:, :, 0:3] - np.repeat(sto.data[-1], PER, axis=0)[:, :, 0:3]).max())
     return {"workload": "lqr_sawyer TrackingLQR: 64 reference trajectories x 2000 steps, 16 perturbed closed-loop rollouts each (1024 systems)",
-            "synthesis_device_ms": sum(ph.values()), "synthesis_phase_ms": ph, "synthesis_e2e_s": synth_wall,
-            "linearisations_per_s_device": NT * (N - 1) / (sum(ph.values()) * 1e-3),
+            "synthesis_device_ms": dev_ms, "synthesis_phase_ms": ph, "synthesis_e2e_s": synth_wall,
+            "linearisations_per_s_device": NT * (N - 1) / (dev_ms * 1e-3),
             "rollout_sim_steps_per_s": B * N / (best * 1e-3), "rollout_ms": best, "final_tracking_error_m": err}
 
 

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(RT) riccati_sweep_kernel(int n, int nu, int N,
 bool riccati_dmma_eligible(int n, int nu);
 int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                               long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
-                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream);
+                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream, int k_hi, int k_lo, int resume);
 
 bool riccati_big_eligible(int n, int nu);
 int riccati_sweep_big_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
@@ -186,11 +186,13 @@ int riccati_project_device(int P, int n, int nu, int ml, const double* A, const 
 
 int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                          long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
-                         int* kexit, int* iters, double* ws, cudaStream_t stream) {
+                         int* kexit, int* iters, double* ws, cudaStream_t stream, int k_hi, int k_lo, int resume) {
+    // k_hi > 0: run only k = k_hi .. k_lo of the sweep (resume != 0: continuing an earlier launch) -- K4 only
     if (nu > 8) { set_error("riccati: more than 8 controlled eqcs is not supported yet"); return CCB_E_UNSUPPORTED; }
+    if (k_hi > 0 && !(riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA"))) { set_error("riccati: partial sweeps need the K4 kernel"); return CCB_E_UNSUPPORTED; }
     if (riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA"))      // K4: FP64 tensor-core sweep, P / Abar resident in shared memory
         return riccati_sweep_dmma_device(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws,
-                                         (long long)riccati_sweep_ws_doubles(n, nu), stream);
+                                         (long long)riccati_sweep_ws_doubles(n, nu), stream, k_hi, k_lo, resume);
     if (n > 108 && riccati_big_eligible(n, nu) && !getenv("CCB_NO_DMMA"))   // K4b: blocked FP64 tensor-core GEMMs on the global workspace
         return riccati_sweep_big_device(S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws,
                                         (long long)riccati_sweep_ws_doubles(n, nu), stream);

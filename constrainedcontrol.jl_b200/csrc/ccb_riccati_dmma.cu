@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                                                                      long long stride_s_D, const double* __restrict__ Q, long long Q_bs,
                                                                      const double* __restrict__ R, long long R_bs, double* __restrict__ Ku,
                                                                      int* __restrict__ kexit, int* __restrict__ iters, double* __restrict__ ws,
-                                                                     long long ws_stride) {
+                                                                     long long ws_stride, int k_hi, int k_lo, int resume) {
+    // k_hi .. k_lo: the part of the sweep this launch runs (k_hi = N - 1, k_lo = 1: all of it).  resume != 0: continue a sweep whose
+    // earlier part ran in a previous launch -- P comes from the global copy, kexit[s] != 0 means the system has already left the loop.
     extern __shared__ __align__(16) double sm[];
     constexpr int NT = 32 * T;
     constexpr bool A_SM = STAGE >= 2, Q_SM = STAGE == 2, POLD_REG = STAGE >= 2;   // what a staged variant keeps on chip
@@ -91,7 +93,12 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     double* po_c = STAGE == 1 ? Asm + (size_t)ra * LD + 2 * t4 : pg_c;
     (void)Pold;
 
-    for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
+    if (resume && kexit[s] != 0) return;                     // broke out of the loop in an earlier launch (block-uniform)
+    if (resume) {
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Ps[(size_t)i * LD + j] = Pg[e]; }
+    } else {
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); const double v = Qs[e]; Ps[(size_t)i * LD + j] = v; Pg[e] = v; }   // lqr.jl:147
+    }
     if (A_SM) {
         const double* A0 = At + s * stride_s_A;
         for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Asm[(size_t)i * LD + j] = A0[e]; if (Q_SM) Qsm[(size_t)i * LD + j] = Qs[e]; }
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     __syncthreads();
 
     int k, it = 0;
-    for (k = N - 1; k >= 1; k--) {                            // lqr.jl:150
+    for (k = k_hi; k >= k_lo; k--) {                          // lqr.jl:150
         it++;
         const double* Ak = At + s * stride_s_A + (size_t)(k - 1) * stride_t_A;
         const double* Dk = D + s * stride_s_D + (size_t)(k - 1) * stride_t_D;
@@ -359,12 +366,17 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         __syncthreads();
         if (brk) break;
     }
+    if (k < k_lo && k_lo > 1) {                                          // this launch's part is done, the sweep is not: park P for the next launch
+        for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Pg[e] = Ps[(size_t)i * LD + j]; }
+        if (tid == 0) { kexit[s] = 0; iters[s] = (resume ? iters[s] : 0) + it; }
+        return;
+    }
     if (k < 1) k = 1;                                                    // a completed loop leaves k == 1
     for (int k2 = k - 1; k2 >= 1; k2--) {                                // lqr.jl:179-181 back-fill
         for (int e = tid; e < nu * n; e += NT) Kout[(size_t)(k2 - 1) * nu * n + e] = Kout[(size_t)k2 * nu * n + e];
         __syncthreads();
     }
-    if (tid == 0) { kexit[s] = k; iters[s] = it; }
+    if (tid == 0) { kexit[s] = k; iters[s] = (resume ? iters[s] : 0) + it; }
 }
 
 size_t dmma_smem_bytes(int n, int T, int stage, bool nu1 = false) {
@@ -375,11 +387,11 @@ size_t dmma_smem_bytes(int n, int T, int stage, bool nu1 = false) {
 template <int T, bool NU1, int STAGE>
 int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D, long long stride_s_A,
                 long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku, int* kexit, int* iters, double* ws,
-                long long ws_stride, cudaStream_t stream) {
+                long long ws_stride, cudaStream_t stream, int k_hi, int k_lo, int resume) {
     const size_t smem = dmma_smem_bytes(n, T, STAGE, NU1);
     CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T, NU1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     riccati_sweep_dmma_kernel<T, NU1, STAGE><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
-                                                             iters, ws, ws_stride);
+                                                             iters, ws, ws_stride, k_hi, k_lo, resume);
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;
@@ -396,12 +408,13 @@ bool riccati_dmma_eligible(int n, int nu) {
 
 int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                               long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
-                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream) {
+                              int* kexit, int* iters, double* ws, long long ws_stride, cudaStream_t stream, int k_hi, int k_lo, int resume) {
     const int T = (n + 7) / 8;
+    if (k_hi <= 0) { k_hi = N - 1; k_lo = 1; resume = 0; }
     const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
     const bool stage_a = !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;
     const bool stage_b = stage_a && stride_t_A == 0;     // ... and, when Ã does not change, Ã in that third matrix with the previous P of my tiles in registers   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
-#define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream
+#define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream, k_hi, k_lo, resume
 #define CCB_DMMA_CASE(TT)                                                                      \
     case TT:                                                                                   \
         if constexpr (TT <= 5) { if (stage) return nu == 1 ? launch_dmma<TT, true, 2>(CCB_DMMA_ARGS) : launch_dmma<TT, false, 2>(CCB_DMMA_ARGS); } \

@@ -15,7 +15,8 @@ int riccati_project_device(int P, int n, int nu, int ml, const double* A, const 
                            double* ws, cudaStream_t stream);
 int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                          long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
-                         int* kexit, int* iters, double* ws, cudaStream_t stream);
+                         int* kexit, int* iters, double* ws, cudaStream_t stream, int k_hi = 0, int k_lo = 0, int resume = 0);
+bool riccati_dmma_eligible(int n, int nu);
 }
 using namespace ccb;
 
@@ -75,7 +76,7 @@ struct Scratch {
 #define CCB_TRY(x) do { int _rc = (x); if (_rc != CCB_OK) return _rc; } while (0)
 
 // device times of the phases of the last synthesis call on this thread (CUDA events on the launching stream)
-thread_local double g_phase_ms[4] = {0, 0, 0, 0};   // linearize (K1 knot solve + K2), project, sweep (K3/K4), reserved
+thread_local double g_phase_ms[4] = {0, 0, 0, 0};   // linearize (K1 knot solve + K2), project, sweep (K3/K4), elapsed total when the phases overlap (else 0)
 struct PhaseTimer {
     cudaEvent_t ev[4];
     PhaseTimer() { for (auto& e : ev) cudaEventCreate(&e); }
@@ -87,6 +88,7 @@ struct PhaseTimer {
             if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
             g_phase_ms[i] = (accumulate ? g_phase_ms[i] : 0.0) + ms;
         }
+        if (!accumulate) g_phase_ms[3] = 0.0;       // only the overlapped tracking pipeline reports a separate total
     }
 };
 
@@ -342,6 +344,17 @@ int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count) {
 // TrackingLQR synthesis on the device for S trajectories.  Ku goes either to the host (Ku_host) or stays in d_Ku_all
 // ([S][N-1][nu][n], allocated by the caller); traj / Ftau are host arrays; d_traj_keep / d_F_keep (optional, device, whole
 // batch) receive copies of the desired trajectory and feed-forward for the controller.
+// [s][k][w] -> [k][s][w]: the step-major layout of the tracking pipeline
+__global__ void step_major_kernel(const double* __restrict__ in, double* __restrict__ out, int cs, int N, int W) {
+    const size_t total = (size_t)cs * N * W;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(e % W);
+        const size_t p = e / W;
+        const int sI = (int)(p % cs), k = (int)(p / cs);
+        out[e] = in[((size_t)sI * N + k) * W + w];
+    }
+}
+
 static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const double* traj, const double* Ftau, const int32_t* eqc, int nu,
                                  const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku_host, double* d_Ku_all,
                                  double* d_traj_keep, double* d_F_keep, int32_t* kexit, int32_t* iters) {
@@ -369,26 +382,101 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
     CCB_TRY(sc.get(&d_ws1, P * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)chunk * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)chunk)); CCB_TRY(sc.get(&d_iters, (size_t)chunk));
+    // k-pipeline (K4 sizes): the sweep consumes the linearisations from k = N-1 downwards and needs ~1 CTA per trajectory, so the
+    // linearisation + projection of the next block of steps runs on a second stream while the sweep works through the previous one
+    // (stream-ordered through events; the sweep is launched once per block and carries P through the global workspace).
+    // Within a pass the per-(trajectory, step) arrays are laid out step-major, p = k * cs + s, so that a block of steps is contiguous.
+    const char* env_pipe = getenv("CCB_TRACK_PIPELINE");
+    const int nblk = std::min(16, (N - 1) / 128);
+    const bool pipeline = riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA") && nblk >= 2 && !(env_pipe && env_pipe[0] == '0');
+    double *d_zs = nullptr, *d_fs = nullptr;      // trajectory-major staging of the inputs when the caller keeps no device copy
+    if (pipeline && !d_traj_keep) CCB_TRY(sc.get(&d_zs, P * nb * 13));
+    if (pipeline && !d_F_keep) CCB_TRY(sc.get(&d_fs, P * nu));
     PhaseTimer pt;
     for (int s0 = 0; s0 < S; s0 += chunk) {
         const int cs = std::min(chunk, S - s0);
         const int Pc = cs * N;
         double* Kdst = d_Ku_all ? d_Ku_all + (size_t)s0 * (N - 1) * nu * n : d_Ku;
-        CCB_CUDA(cudaMemcpy(d_zd, traj + (size_t)s0 * N * nb * 13, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
-        CCB_CUDA(cudaMemcpy(d_Fd, Ftau + (size_t)s0 * N * nu, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
-        if (d_traj_keep) CCB_CUDA(cudaMemcpy(d_traj_keep + (size_t)s0 * N * nb * 13, d_zd, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyDeviceToDevice));
-        if (d_F_keep) CCB_CUDA(cudaMemcpy(d_F_keep + (size_t)s0 * N * nu, d_Fd, (size_t)Pc * nu * sizeof(double), cudaMemcpyDeviceToDevice));
+        const double* h_traj = traj + (size_t)s0 * N * nb * 13;
+        const double* h_F = Ftau + (size_t)s0 * N * nu;
+        if (d_traj_keep) CCB_CUDA(cudaMemcpy(d_traj_keep + (size_t)s0 * N * nb * 13, h_traj, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
+        if (d_F_keep) CCB_CUDA(cudaMemcpy(d_F_keep + (size_t)s0 * N * nu, h_F, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
         CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)Pc * ml, 1) * sizeof(double)));
-        pt.mark(0);
-        CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
-        pt.mark(1);
-        CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
-        pt.mark(2);
-        CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
-                                     0, Kdst, d_kexit, d_iters, d_ws2, 0));
-        pt.mark(3);
-        CCB_CUDA(cudaDeviceSynchronize());
-        pt.finish(s0 > 0);
+        if (!pipeline) {
+            CCB_CUDA(cudaMemcpy(d_zd, h_traj, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice));
+            CCB_CUDA(cudaMemcpy(d_Fd, h_F, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice));
+            pt.mark(0);
+            CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
+            pt.mark(1);
+            CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+            pt.mark(2);
+            CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
+                                         0, Kdst, d_kexit, d_iters, d_ws2, 0));
+            pt.mark(3);
+            CCB_CUDA(cudaDeviceSynchronize());
+            pt.finish(s0 > 0);
+            if (s0 == 0) g_phase_ms[3] = 0.0;
+        } else {
+            // step-major copies: row k of trajectory s goes to p = k * cs + s (contiguous upload, transposed on the device)
+            const double* src_z = d_traj_keep ? d_traj_keep + (size_t)s0 * N * nb * 13 : nullptr;
+            const double* src_f = d_F_keep ? d_F_keep + (size_t)s0 * N * nu : nullptr;
+            if (!src_z) { CCB_CUDA(cudaMemcpy(d_zs, h_traj, (size_t)Pc * nb * 13 * sizeof(double), cudaMemcpyHostToDevice)); src_z = d_zs; }
+            if (!src_f) { CCB_CUDA(cudaMemcpy(d_fs, h_F, (size_t)Pc * nu * sizeof(double), cudaMemcpyHostToDevice)); src_f = d_fs; }
+            step_major_kernel<<<1184, 256>>>(src_z, d_zd, cs, N, nb * 13);
+            step_major_kernel<<<296, 256>>>(src_f, d_Fd, cs, N, nu);
+            g_launches += 2;
+            CCB_CUDA(cudaGetLastError());
+            CCB_CUDA(cudaDeviceSynchronize());
+            cudaStream_t sa = nullptr, sb = nullptr;
+            std::vector<cudaEvent_t> ev;       // per block: lin start, lin end / proj start, proj end, sweep start, sweep end
+            auto cleanup = [&]() {
+                for (auto e : ev) cudaEventDestroy(e);
+                if (sa) cudaStreamDestroy(sa);
+                if (sb) cudaStreamDestroy(sb);
+            };
+            auto bail = [&](int rc) { cudaDeviceSynchronize(); cleanup(); return rc; };
+            if (cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking) != cudaSuccess)
+                return bail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+            ev.resize((size_t)5 * nblk);
+            for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaEventCreate"));
+            const int E = N - 1;                         // entries 0 .. N-2 are used (entry k-1 is the linearisation at step k)
+            int rc = CCB_OK;
+            for (int c = nblk - 1; c >= 0 && rc == CCB_OK; c--) {
+                const int e_lo = (int)((long long)E * c / nblk), e_hi = (int)((long long)E * (c + 1) / nblk);     // [e_lo, e_hi)
+                const size_t off = (size_t)e_lo * cs;
+                const int Pb = (e_hi - e_lo) * cs;
+                cudaEvent_t* e5 = &ev[(size_t)5 * c];
+                cudaEventRecord(e5[0], sa);
+                rc = linearize_device(&m->h, device, Pb, d_zd + off * nb * 13, d_Fd + off * nu, d_eqc, nu, opts, d_A + off * n * n, d_Bu + off * n * nu,
+                                      d_Bl + off * n * ml, d_G + off * ml * n, d_lam + off * ml, d_s + off * nb * 6, d_status + off, sa);
+                if (rc != CCB_OK) break;
+                cudaEventRecord(e5[1], sa);
+                rc = riccati_project_device(Pb, n, nu, ml, d_A + off * n * n, d_Bu + off * n * nu, d_Bl + off * n * ml, d_G + off * ml * n, d_At + off * n * n,
+                                            d_D + off * n * nu, d_ws1 + off * riccati_project_ws_doubles(n, nu, ml), sa);
+                if (rc != CCB_OK) break;
+                cudaEventRecord(e5[2], sa);
+                cudaStreamWaitEvent(sb, e5[2], 0);
+                cudaEventRecord(e5[3], sb);
+                rc = riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)cs * n * n, (long long)cs * n * nu, (long long)n * n, (long long)n * nu, d_Q, 0, d_R, 0,
+                                          Kdst, d_kexit, d_iters, d_ws2, sb, e_hi, e_lo + 1, c != nblk - 1);
+                cudaEventRecord(e5[4], sb);
+            }
+            if (rc != CCB_OK) return bail(rc);
+            if (cudaDeviceSynchronize() != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "tracking pipeline"));
+            double ph[3] = {0, 0, 0};
+            for (int c = 0; c < nblk; c++) {
+                float ms;
+                if (cudaEventElapsedTime(&ms, ev[5 * c], ev[5 * c + 1]) == cudaSuccess) ph[0] += ms;
+                if (cudaEventElapsedTime(&ms, ev[5 * c + 1], ev[5 * c + 2]) == cudaSuccess) ph[1] += ms;
+                if (cudaEventElapsedTime(&ms, ev[5 * c + 3], ev[5 * c + 4]) == cudaSuccess) ph[2] += ms;
+            }
+            float total = 0.f;
+            cudaEventElapsedTime(&total, ev[(size_t)5 * (nblk - 1)], ev[4]);      // first linearisation start .. last sweep end
+            for (int i = 0; i < 3; i++) g_phase_ms[i] = (s0 > 0 ? g_phase_ms[i] : 0.0) + ph[i];
+            g_phase_ms[3] = (s0 > 0 ? g_phase_ms[3] : 0.0) + total;
+            cudaGetLastError();
+            cleanup();
+        }
         if (Ku_host) CCB_CUDA(cudaMemcpy(Ku_host + (size_t)s0 * (N - 1) * nu * n, Kdst, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
         if (kexit) CCB_CUDA(cudaMemcpy(kexit + s0, d_kexit, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
         if (iters) CCB_CUDA(cudaMemcpy(iters + s0, d_iters, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));

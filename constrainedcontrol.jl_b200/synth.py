@@ -94,3 +94,10 @@ def phase_ms():
     out = (C.c_double * 4)()
     check(_lib.lib().ccb_synth_phase_ms(out))
     return dict(linearize=out[0], project=out[1], sweep=out[2])
+
+
+def phase_total_ms():
+    """elapsed device time (ms) of the last synthesis call: the separate total of an overlapped call (TrackingLQR pipeline), else the sum of the phases"""
+    out = (C.c_double * 4)()
+    check(_lib.lib().ccb_synth_phase_ms(out))
+    return out[3] if out[3] > 0 else out[0] + out[1] + out[2]

@@ -237,7 +237,8 @@ int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m,
 
 /* Device time (ms, CUDA events on the launching stream) of the phases of the last ccb_dlqr / ccb_lqr_synthesize /
  * ccb_tracking_synthesize call on the calling thread: out[0] linearisation (K1 knot solve + K2), out[1] constraint projection,
- * out[2] Riccati sweep (K3 / K4), out[3] reserved.  Measurement aid for bench.py (no reference counterpart). */
+ * out[2] Riccati sweep (K3 / K4), out[3] elapsed device time of the whole call when the phases overlap (the TrackingLQR
+ * pipeline: out[0..2] are then per-phase sums of overlapping work), else 0.  Measurement aid for bench.py (no reference counterpart). */
 int ccb_synth_phase_ms(double out[4]);
 
 #ifdef __cplusplus

@@ -24,7 +24,7 @@ t0 = time.time()
 tl = cc.TrackingLQR(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"])
 t1 = time.time()
 ph = cc.synth.phase_ms()
-print(f"TrackingLQR synthesis: {NT} trajectories x {N - 1} linearisations+Riccati steps: {t1 - t0:.3f} s e2e; device phases {ph}; kexit {tl.kexit[:4]}", flush=True)
+print(f"TrackingLQR synthesis: {NT} trajectories x {N - 1} linearisations+Riccati steps: {t1 - t0:.3f} s e2e; device phases {ph}, elapsed {cc.synth.phase_total_ms():.1f} ms; kexit {tl.kexit[:4]}", flush=True)
 B = NT * PER
 stp = np.repeat(st0, PER, axis=0)
 pert = np.zeros((B, 7))
