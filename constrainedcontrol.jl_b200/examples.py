@@ -182,6 +182,65 @@ def deltabot(dt: float = 0.01, reg: float = 1e-10):
     return mech, cfg
 
 
+def deltabot_initial_conditions(s1: int = 101, s2: int = 101, L: float = 1.0):
+    """examples/lqr_deltabot.jl:57-145: the grid of platform positions the two legs can reach and the leg angles that realise them.
+    Returns (A [nc][2] platform (y, z), anglesl [nc][2], anglesr [nc][2]); 1973 valid positions for the example's 101 x 101 grid."""
+    ppz3 = L / 4 * math.sqrt(2)
+    coords = []
+    for i in range(1, s1 + 1):                                      # :64-86
+        ppz = -1.5 * L + 3 * L * (i - 1) / (s1 - 1)
+        if ppz < 0:
+            continue
+        for j in range(1, s2 + 1):
+            ppy = -1.5 * L + 3 * L * (j - 1) / (s2 - 1)
+            ppr = np.array([0.0, ppy + ppz3, ppz]); ppl = np.array([0.0, ppy - ppz3, ppz])
+            if np.linalg.norm(ppr) <= 1.5 * L and np.linalg.norm(ppl) <= 1.5 * L and np.linalg.norm(ppr) >= 0.5 * L and np.linalg.norm(ppl) >= 0.5 * L:
+                coords.append((ppy, ppz))
+    A = np.array(coords)
+    nc = A.shape[0]
+    anglesl = np.zeros((nc, 2)); anglesr = np.zeros((nc, 2))
+    a, b = L, L / 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(nc):                                         # :100-141
+            ppr = A[i] + np.array([ppz3, 0.0]); ppl = A[i] - np.array([ppz3, 0.0])
+            cl = np.linalg.norm(ppl)
+            bl = math.acos((a * a + cl * cl - b * b) / (2 * a * cl)); gl = math.acos((a * a + b * b - cl * cl) / (2 * a * b))
+            dl = abs(math.atan(ppl[0] / ppl[1])) if ppl[1] != 0 else math.pi / 2
+            cr = np.linalg.norm(ppr)
+            br = math.acos((a * a + cr * cr - b * b) / (2 * a * cr)); gr = math.acos((a * a + b * b - cr * cr) / (2 * a * b))
+            dr = abs(math.atan(ppr[0] / ppr[1])) if ppr[1] != 0 else math.pi / 2
+            if ppl[0] <= 0 and ppl[1] >= 0: anglesl[i] = [dl + bl, -math.pi + gl]
+            elif ppl[0] >= 0 and ppl[1] >= 0: anglesl[i] = [-dl + bl, -math.pi + gl]
+            elif ppl[0] >= 0 and ppl[1] <= 0: anglesl[i] = [-math.pi + dl - bl, math.pi - gl]
+            elif ppl[0] <= 0 and ppl[1] <= 0: anglesl[i] = [-math.pi - dl - bl, math.pi - gl]
+            if ppr[0] <= 0 and ppr[1] >= 0: anglesr[i] = [dr - br, math.pi - gr]
+            elif ppr[0] >= 0 and ppr[1] >= 0: anglesr[i] = [-dr - br, math.pi - gr]
+            elif ppr[0] >= 0 and ppr[1] <= 0: anglesr[i] = [-math.pi + dr + br, -math.pi + gr]
+            elif ppr[0] <= 0 and ppr[1] <= 0: anglesr[i] = [-math.pi - dr + br, -math.pi + gr]
+    return A, anglesl, anglesr
+
+
+def deltabot_states(mech: Mechanism, B: int, grid: int = 105):
+    """[B][5][13]: the first B valid initial conditions of the example's grid construction (lqr_deltabot.jl:147-152, one `i` per system).
+    SURVEY 8(d) C5: a 105 x 105 grid has more than 2048 valid platform positions."""
+    L = 1.0
+    pll = np.array([0.0, 0.0, L / 2]); pul = np.array([0.0, 0.0, L / 4])
+    A, al, ar = deltabot_initial_conditions(grid, grid, L)
+    assert A.shape[0] >= B, f"grid {grid} x {grid} has only {A.shape[0]} valid positions"
+    lowerlegl, lowerlegr, upperlegl, upperlegr, platform = mech.bodies
+    keep = mech.state_vector()
+    out = np.zeros((B, mech.nb, 13))
+    for i in range(B):
+        setPosition(mech.origin, lowerlegl, p2=-pll, dq=RotX(al[i][0]))
+        setPosition(mech.origin, lowerlegr, p2=-pll, dq=RotX(ar[i][0]))
+        setPosition(lowerlegl, upperlegl, p1=pll, p2=-pul, dq=RotX(al[i][1]))
+        setPosition(lowerlegr, upperlegr, p1=pll, p2=-pul, dq=RotX(ar[i][1]))
+        setPosition(mech.origin, platform, p1=np.array([0.0, A[i][0], A[i][1]]), dq=RotX(math.pi / 2))
+        out[i] = mech.state_vector()
+    mech.set_state_vector(keep)
+    return out
+
+
 def sawyer(description_path: str, dt: float = 0.01):
     """examples/lqr_sawyer.jl:8-29: sawyer_arm.urdf, floating=false, g=0; Q = 1000 I12 x 7, R = 1 x 7, horizon 20.
     `description_path` is the URDF itself or the parsed JSON fixture (tests/golden/sawyer_arm.json)."""

@@ -201,6 +201,32 @@ def test_c5_deltabot_closed_chain(cc, orc):
     assert np.abs(fin[0, 4, 0:3] - st0[0, 4, 0:3]).max() < 5e-3   # the feed-forward holds the platform (nearly) in place
 
 
+def test_c5_deltabot_lqr_from_the_example_grid(cc, orc):
+    """C5 as SURVEY 8(d) states it: infinite-horizon LQR of examples/lqr_deltabot.jl started from the example's own grid of platform
+    positions.  Parity with the oracle on a strided sample (same gain table in both), failure parity, properties at the full size."""
+    mech, cfg = cc.examples.deltabot()
+    om = orc.OracleMech(mech.desc())
+    eqc_idx = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], math.inf, xd=cfg["xd"], qd=cfg["qd"], Ftaud=cfg["Ftaud"])
+    K = lqr.K[0, 0]
+    B = 2048
+    st0 = cc.examples.deltabot_states(mech, B)
+    steps = 300
+    sto, fin, status = cc.simulate(mech, steps * mech.dt, lqr, record=False, states=st0, return_status=True)
+    ok = status > 0
+    assert ok.sum() > B // 2                                    # far-away starts may leave the region of attraction; most do not
+    assert np.abs(np.linalg.norm(fin[ok][:, :, 3:7], axis=2) - 1.0).max() < 1e-12
+    assert constraint_violation(cc, mech, fin[ok][::53]) < 1e-8
+    # oracle on every 64th system: the same systems fail, the others agree
+    sel = np.arange(0, B, 64)
+    co = om.make_ctrl(len(sel), kind="lqr_inf", eqc=eqc_idx, K=K, zd=zd_of(mech, cfg), Fd=np.array(cfg["Ftaud"]))
+    r = om.simulate(st0[sel], steps, ctrl=co, record=False, nthreads=8)
+    o_ok = r["iters"] > 0
+    assert np.array_equal(o_ok, ok[sel])
+    both = o_ok & ok[sel]
+    assert rel_err(fin[sel][both], r["states"][both]) < 1e-6     # rank-deficient KKT + closed loop over 300 steps: noise-limited at ~reg level
+
+
 def test_c5_pid_sweep_properties(cc, orc):
     # examples/pid_doublependulum.jl over a 32 x 32 grid of goal pairs (1024 systems), 1000 steps
     mech, cfg = cc.examples.doublependulum()

@@ -83,3 +83,22 @@ def test_are_util_batches_and_broadcasts_without_touching_the_device(cc):
     import pytest
     with pytest.raises(AssertionError):
         cc.util._batched(A, np.ones((3, 2, 1)), Q, [[1.0]])      # batch sizes differ
+
+
+def test_deltabot_initial_condition_grid_matches_the_example(cc):
+    """examples/lqr_deltabot.jl:57-145: the 101 x 101 grid has 1973 reachable platform positions; every initial
+    condition built from it closes both kinematic loops"""
+    import numpy as np
+    A, al, ar = cc.examples.deltabot_initial_conditions()
+    assert A.shape == (1973, 2) and (A[:, 1] >= 0).all()
+    mech, _ = cc.examples.deltabot()
+    nominal = mech.state_vector().copy()
+    st = cc.examples.deltabot_states(mech, 2048)
+    assert np.array_equal(mech.state_vector(), nominal)            # the helper leaves the mechanism where it found it
+    worst = 0.0
+    for s in st[::23]:
+        mech.set_state_vector(s)
+        worst = max(worst, float(np.abs(mech.constraint_values()).max()))
+    mech.set_state_vector(nominal)
+    assert worst < 1e-12
+    assert np.unique(st.reshape(2048, -1), axis=0).shape[0] == 2048

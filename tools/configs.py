@@ -110,10 +110,8 @@ if want("C4"):
 if want("C5a"):
     # lqr_deltabot: closed chain (2 loops, rank-deficient constraint set); gravity-compensating feed-forward, horizon Inf
     mech, cfg = cc.examples.deltabot()
-    def st_fn(B):
-        rng = np.random.default_rng(5)
-        st = mech.batch_states(B)
-        return st
+    def st_fn(B):          # the example's own grid of reachable platform positions (lqr_deltabot.jl:57-152), first B of a 105 x 105 grid
+        return cc.examples.deltabot_states(mech, B) if B > 8 else mech.batch_states(B)
     try:
         run_lqr_config("C5 lqr_deltabot", mech, cfg, st_fn, 2048, 1000, math.inf, parity_B=4, parity_steps=100, synth_S=64)
     except Exception as e:
