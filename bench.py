@@ -115,13 +115,24 @@ def synthesis_bench(cc, torch, dev, peaks):
         nu, n = len(cfg["eqcids"]), 12 * mech.nb
         rng = np.random.default_rng(2)
         qs = np.exp(rng.uniform(np.log(0.1), np.log(10), S)); rs = np.exp(rng.uniform(np.log(0.1), np.log(10), S))
+        xd, qd = cfg["xd"], cfg.get("qd")
+        if name == "sawyer":
+            # 1024 distinct setpoints, joint angles ~ U(-0.5, 0.5) rad (seed 3), maximal coordinates by forward kinematics;
+            # g = 0, so every configuration is an equilibrium with zero feed-forward.  Weights as in examples/lqr_sawyer.jl.
+            r3 = np.random.default_rng(3)
+            xd = np.zeros((S, mech.nb, 3)); qd = np.zeros((S, mech.nb, 4))
+            for s_ in range(S):
+                cc.urdf.zero_configuration(mech, {i: r3.uniform(-0.5, 0.5) for i in range(mech.ne)})
+                stv = mech.state_vector()
+                xd[s_] = stv[:, 0:3]; qd[s_] = stv[:, 3:7]
+            cc.urdf.zero_configuration(mech)
+            qs[:] = 1.0; rs[:] = 1.0
         Qb = cc.blockdiag(cfg["Q"])[None] * qs[:, None, None]; Rb = cc.blockdiag(cfg["R"])[None] * rs[:, None, None]
-        xd = cfg["xd"]
         best = None
         for rep in range(2):
             torch.cuda.synchronize()
             t0 = time.time()
-            lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], None, None, horizon, xd=xd, qd=cfg.get("qd"), Q_batch=Qb, R_batch=Rb, device=dev)
+            lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], None, None, horizon, xd=xd, qd=qd, Q_batch=Qb, R_batch=Rb, device=dev)
             wall = time.time() - t0
             ph = cc.synth.phase_ms()
             if best is None or wall < best[0]:
@@ -140,7 +151,8 @@ def synthesis_bench(cc, torch, dev, peaks):
         tf = S * iters * F_ref / (ph["sweep"] * 1e-3) / 1e12
         tf_exec = S * iters * F_exec / (ph["sweep"] * 1e-3) / 1e12
         peak = peaks.get("dmma_m8n8k4_tflops")
-        out[name] = {"batch": S, "n": n, "nu": nu, "m_lambda": mech.ml, "horizon_steps": int(math.ceil(horizon / mech.dt)), "riccati_iters_mean": iters,
+        out[name] = {"batch": S, "problems": "distinct setpoints (joint angles ~ U(-0.5, 0.5) rad), weights of the example" if name == "sawyer" else "one setpoint, distinct (Q, R) scales ~ logU(0.1, 10)",
+                     "n": n, "nu": nu, "m_lambda": mech.ml, "horizon_steps": int(math.ceil(horizon / mech.dt)), "riccati_iters_mean": iters,
                      "syntheses_per_s_device": S / dev_s, "syntheses_per_s_e2e": S / wall, "phase_ms": ph,
                      "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": (tf / peak) if peak else None,
                                   "flops_per_iteration": F_ref, "executed_tflops": tf_exec, "executed_frac": (tf_exec / peak) if peak else None,
