@@ -22,13 +22,22 @@ using namespace ccb;
 
 namespace {
 
-// Device scratch for one API call.  Small requests are carved from a per-device arena that persists across calls (cudaMalloc /
-// cudaFree synchronise the device and cost more than a cartpole synthesis batch); requests that do not fit (TrackingLQR batches:
-// tens of GB) fall back to cudaMalloc and are released when the call returns.  Not thread safe across calls on one device, like
-// the handles themselves.
+// Device scratch for one API call.  Requests are carved from a per-device arena that persists across calls (cudaMalloc / cudaFree
+// synchronise the device and cost more than a cartpole synthesis batch, and ~0.1 s for the tens of GB of a TrackingLQR batch); the
+// arena grows after a call that did not fit, up to a quarter of the device memory (CCB_ARENA_MAX_GB overrides), requests beyond
+// that fall back to cudaMalloc and are released when the call returns.  ccb_scratch_release() gives the arenas back.  Not thread
+// safe across calls on one device, like the handles themselves.
 struct Arena { char* base = nullptr; size_t cap = 0, off = 0, want = 0; };
 static std::map<int, Arena> g_arenas;
-constexpr size_t kArenaMax = (size_t)4 << 30;
+static size_t arena_max() {
+    static size_t v = 0;
+    if (v) return v;
+    if (const char* e = getenv("CCB_ARENA_MAX_GB")) { v = (size_t)std::max(1.0, atof(e)) << 30; return v; }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = (size_t)16 << 30; }
+    v = std::max<size_t>((size_t)4 << 30, total_b / 4);
+    return v;
+}
 
 struct Scratch {
     std::vector<void*> ptrs;
@@ -42,7 +51,7 @@ struct Scratch {
         for (void* p : ptrs) cudaFree(p);
         if (!ar) return;
         ar->off = start;
-        ar->want = std::max(ar->want, std::min(asked, kArenaMax));
+        ar->want = std::max(ar->want, asked <= arena_max() ? asked : ar->want);
         if (start == 0 && ar->want > ar->cap) {      // grow for the next call
             cudaFree(ar->base);
             ar->base = nullptr; ar->cap = 0;
@@ -195,6 +204,16 @@ int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m,
     if (K) CCB_CUDA(cudaMemcpy(K, d_K, (size_t)S * m * n * sizeof(double), cudaMemcpyDeviceToHost));
     if (iters) CCB_CUDA(cudaMemcpy(iters, d_it, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
     if (status) CCB_CUDA(cudaMemcpy(status, d_st, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost));
+    return CCB_OK;
+}
+
+int ccb_scratch_release(void) {
+    for (auto& kv : g_arenas) {
+        if (kv.second.off != 0) { set_error("ccb_scratch_release: a call is in flight"); return CCB_E_INVALID; }
+        if (kv.second.base) { cudaSetDevice(kv.first); cudaFree(kv.second.base); }
+        kv.second = Arena();
+    }
+    cudaGetLastError();
     return CCB_OK;
 }
 

@@ -101,3 +101,8 @@ def phase_total_ms():
     out = (C.c_double * 4)()
     check(_lib.lib().ccb_synth_phase_ms(out))
     return out[3] if out[3] > 0 else out[0] + out[1] + out[2]
+
+
+def release_scratch():
+    """give the library's persistent device scratch back to the driver (ccb_scratch_release)"""
+    check(_lib.lib().ccb_scratch_release())

@@ -235,6 +235,10 @@ int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const
 int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m, const double* A, const double* B, const double* Q,
                   const double* R, double* X, double* K, int32_t* iters, int32_t* status);
 
+/* The synthesis calls keep their device scratch (up to a quarter of the device memory; CCB_ARENA_MAX_GB overrides) between calls so
+ * that repeated syntheses do not pay cudaMalloc / cudaFree again; this gives it back.  No reference counterpart (Julia's GC). */
+int ccb_scratch_release(void);
+
 /* Device time (ms, CUDA events on the launching stream) of the phases of the last ccb_dlqr / ccb_lqr_synthesize /
  * ccb_tracking_synthesize call on the calling thread: out[0] linearisation (K1 knot solve + K2), out[1] constraint projection,
  * out[2] Riccati sweep (K3 / K4), out[3] elapsed device time of the whole call when the phases overlap (the TrackingLQR
