@@ -349,4 +349,7 @@ lqr(A, B, Q, R; kw...) = are_solve(1, A, B, Q, R; wantX = false, wantK = true, k
 dlqr(A, B, Q, R; kw...) = are_solve(0, A, B, Q, R; wantX = false, wantK = true, kw...)       # util.jl:45-49
 dlqr(A, B, Q, R, Δt::Real; kw...) = dlqr(A .* Δt .+ Matrix{Float64}(I, size(A, 1), size(A, 1)), B .* Δt, Q .* Δt, R .* Δt; kw...)   # util.jl:51-59
 
+"give the library's persistent device scratch (kept between synthesis calls) back to the driver"
+release_scratch() = check(ccall((:ccb_scratch_release, libccb), Cint, ()))
+
 end # module
