@@ -205,6 +205,33 @@ class Controller:
             pass
 
 
+class TableLQR(Controller):
+    """finite-horizon LQR (control_lqr!, lqr.jl:89-114) over a device-resident gain table filled by dist.PeerGainTable"""
+
+    kind = CTRL_LQR_FIN
+
+    def __init__(self, table):
+        super().__init__()
+        self.mech, self.table = table.mech, table
+        self._h = {}
+
+    def device_handle(self, B: int, device: int):
+        t = self.table
+        if B != t.S or device != t.device:
+            raise CcbError(f"TableLQR: the table holds {t.S} systems on device {t.device}")
+        if device not in self._h:
+            h = C.c_void_p()
+            check(_lib.lib().ccb_lqr_ctrl_from_table(handle(self.mech).h, C.c_int32(device), C.c_int32(t.S), C.c_int32(t.N), C.c_int32(t.nu), ptr(t.eqc_idx),
+                                                    t.ptr, ptr(t.zd_all), ptr(t.Fd_all), C.byref(h)))
+            self._h[device] = h
+        return self._h[device]
+
+    def invalidate(self):
+        for h in self._h.values():
+            _lib.lib().ccb_ctrl_destroy(h)
+        self._h = {}
+
+
 def _stride(a: np.ndarray, per: int, B: int) -> int:
     if a.size == per:
         return 0

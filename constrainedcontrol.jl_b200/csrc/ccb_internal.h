@@ -148,6 +148,12 @@ int launch_rollout_chain(const DevMech& M, const DevCtrl& C, const SimArgs& a, c
 int rollout_smem_bytes(const DevMech& M, int lanes);
 int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream);
 bool mw_kernel_eligible(const DevMech& M);
+// Extra destinations of the gain rows a Riccati sweep produces: device tables laid out [S_total][N-1][nu][n] (this rank's own and
+// peer GPUs' tables mapped through CUDA IPC); system s of the launch goes to index s_offset + s of every table.  The all-gather of
+// SURVEY 8(e) fused into the sweep: the rows leave over NVLink while the recursion runs.  Set for the calling thread by
+// ccb_lqr_synthesize_peers (ccb_synth.cu), read by the K4 launcher; n == 0: none.
+struct PeerTables { double* t[8]; int n; long long s_offset; };
+extern thread_local PeerTables g_peer_tables;
 // K5 (ccb_are.cu): kind 0 DARE, 1 CARE; device pointers; ws >= S * are_ws_doubles(n) doubles
 size_t are_ws_doubles(int n);
 int are_sda_device(int kind, int S, int n, int m, const double* A, const double* B, const double* Q, const double* R, double tol, int maxit, double* X,

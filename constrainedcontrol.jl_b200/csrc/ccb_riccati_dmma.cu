@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                                                                      long long stride_s_D, const double* __restrict__ Q, long long Q_bs,
                                                                      const double* __restrict__ R, long long R_bs, double* __restrict__ Ku,
                                                                      int* __restrict__ kexit, int* __restrict__ iters, double* __restrict__ ws,
-                                                                     long long ws_stride, int k_hi, int k_lo, int resume) {
+                                                                     long long ws_stride, int k_hi, int k_lo, int resume, const PeerTables peers) {
     // k_hi .. k_lo: the part of the sweep this launch runs (k_hi = N - 1, k_lo = 1: all of it).  resume != 0: continue a sweep whose
     // earlier part ran in a previous launch -- P comes from the global copy, kexit[s] != 0 means the system has already left the loop.
     extern __shared__ __align__(16) double sm[];
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     const double* Qs = Q + s * Q_bs;
     const double* Rg = R + s * R_bs;
     double* Kout = Ku + s * (size_t)(N - 1) * nu * n;
+    const size_t kbase = (size_t)(peers.s_offset + (long long)s) * (size_t)(N - 1) * nu * n;      // my system's slot in the peer tables
     const int i0 = 8 * w;                                     // my strip
     const int ra = min(i0 + g, n - 1);                        // clamped row of my A fragments / C fragments
     const bool row_ok = i0 + g < n;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 const double x0 = Kk[c] * inv;
                 Kk[c] = x0;
                 Kout[(size_t)(k - 1) * n + c] = x0;                          // lqr.jl:162-164
+                for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k - 1) * n + c] = x0;      // ... and into the peer tables (NVLink stores)
                 RK[c] = r00 * x0;
             }
         } else {
@@ -231,7 +233,10 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     Kk[i * LD + c] = x[i];
-                    if (i < nu) Kout[(size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];      // lqr.jl:162-164
+                    if (i < nu) {
+                        Kout[(size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];      // lqr.jl:162-164
+                        for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];
+                    }
                     double acc = 0.0;
 #pragma unroll
                     for (int j = 0; j < 8; j++) acc = fma(Rs[i * 8 + j], x[j], acc);
@@ -373,7 +378,11 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     }
     if (k < 1) k = 1;                                                    // a completed loop leaves k == 1
     for (int k2 = k - 1; k2 >= 1; k2--) {                                // lqr.jl:179-181 back-fill
-        for (int e = tid; e < nu * n; e += NT) Kout[(size_t)(k2 - 1) * nu * n + e] = Kout[(size_t)k2 * nu * n + e];
+        for (int e = tid; e < nu * n; e += NT) {
+            const double v = Kout[(size_t)k2 * nu * n + e];
+            Kout[(size_t)(k2 - 1) * nu * n + e] = v;
+            for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k2 - 1) * nu * n + e] = v;
+        }
         __syncthreads();
     }
     if (tid == 0) { kexit[s] = k; iters[s] = (resume ? iters[s] : 0) + it; }
@@ -391,7 +400,7 @@ int launch_dmma(int S, int n, int nu, int N, const double* At, const double* D, 
     const size_t smem = dmma_smem_bytes(n, T, STAGE, NU1);
     CCB_CUDA(cudaFuncSetAttribute(riccati_sweep_dmma_kernel<T, NU1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     riccati_sweep_dmma_kernel<T, NU1, STAGE><<<S, 32 * T, smem, stream>>>(n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit,
-                                                             iters, ws, ws_stride, k_hi, k_lo, resume);
+                                                             iters, ws, ws_stride, k_hi, k_lo, resume, g_peer_tables);
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;

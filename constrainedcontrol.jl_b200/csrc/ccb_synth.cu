@@ -19,6 +19,7 @@ int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const do
 bool riccati_dmma_eligible(int n, int nu);
 }
 using namespace ccb;
+namespace ccb { thread_local PeerTables g_peer_tables = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0, 0}; }
 
 namespace {
 
@@ -332,6 +333,114 @@ int ccb_lqr_create(ccb_mech* m, int32_t device, int32_t S, const double* zd, con
     c->allocs.push_back(d_Ku);
     c->v.K = d_Ku;
     d_Ku = nullptr;
+    void *p_eqc = nullptr, *p_zd = nullptr, *p_Fd = nullptr;
+    if (cudaMalloc(&p_eqc, nu * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_eqc);
+    if (cudaMalloc(&p_zd, (size_t)S * nb * 13 * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_zd);
+    if (cudaMalloc(&p_Fd, (size_t)S * nu * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_Fd);
+    if (cudaMemcpy(p_eqc, eqc, nu * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_zd, zd, (size_t)S * nb * 13 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_Fd, Fd, (size_t)S * nu * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
+    c->v.eqc = (const int*)p_eqc;
+    c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)nb * 13 : 0;
+    c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)nu : 0;
+    *out = c;
+    return CCB_OK;
+}
+
+// ---- gain tables that peer GPUs of the node can write into (CUDA IPC) and the synthesis that fills them: SURVEY 8(e)'s all-gather of
+// gain tables fused into the Riccati sweep (the rows leave over NVLink as plain stores while the recursion runs)
+int ccb_gains_alloc(int32_t device, int64_t count, double** dptr, unsigned char ipc_handle[64]) {
+    if (count < 1 || !dptr) { set_error("ccb_gains_alloc: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_device(device, "ccb_gains_alloc"));
+    void* p = nullptr;
+    CCB_CUDA(cudaMalloc(&p, (size_t)count * sizeof(double)));
+    if (ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, p);
+        if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+        std::memcpy(ipc_handle, &h, 64);
+    }
+    *dptr = (double*)p;
+    return CCB_OK;
+}
+
+int ccb_gains_open(int32_t device, const unsigned char ipc_handle[64], double** dptr) {
+    if (!ipc_handle || !dptr) { set_error("ccb_gains_open: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_device(device, "ccb_gains_open"));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    CCB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = (double*)p;
+    return CCB_OK;
+}
+
+int ccb_gains_close(double* dptr) {
+    if (dptr) CCB_CUDA(cudaIpcCloseMemHandle(dptr));
+    return CCB_OK;
+}
+
+int ccb_gains_free(double* dptr) {
+    if (dptr) CCB_CUDA(cudaFree(dptr));
+    return CCB_OK;
+}
+
+int ccb_gains_read(int32_t device, const double* dptr, int64_t offset, double* host, int64_t count) {
+    if (!dptr || !host || count < 0 || offset < 0) { set_error("ccb_gains_read: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_device(device, "ccb_gains_read"));
+    CCB_CUDA(cudaMemcpy(host, dptr + offset, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
+    return CCB_OK;
+}
+
+int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
+                             const double* Q, int64_t Q_bs, const double* R, int64_t R_bs, int32_t N, const ccb_sim_opts* opts, int32_t ntables,
+                             double* const* tables, int64_t s_offset, int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || !zd || nu < 1 || !Fd || !eqc || !Q || !R || N < 2 || ntables < 1 || ntables > 8 || !tables || s_offset < 0) {
+        set_error("ccb_lqr_synthesize_peers: bad arguments (1..8 tables)");
+        return CCB_E_INVALID;
+    }
+    if (m->h.ml == 0) { set_error("ccb_lqr_synthesize_peers: mechanism without joints is out of scope"); return CCB_E_UNSUPPORTED; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_lqr_synthesize_peers"));
+    CCB_TRY(check_device(device, "ccb_lqr_synthesize_peers"));
+    const int n = 12 * m->h.nb;
+    const size_t per = (size_t)(N - 1) * nu * n;
+    const bool fused = riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA");     // K4 stores the rows into the tables itself
+    if (fused) {
+        g_peer_tables.n = ntables;
+        g_peer_tables.s_offset = s_offset;
+        for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
+    }
+    double* d_Ku = nullptr;
+    int rc = lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters);
+    g_peer_tables.n = 0;
+    if (rc != CCB_OK) return rc;
+    if (!fused) {                      // other kernels: the finished shard is copied to every table (peer copies over NVLink)
+        for (int i = 0; i < ntables && rc == CCB_OK; i++)
+            if (cudaMemcpy(tables[i] + (size_t)s_offset * per, d_Ku, (size_t)S * per * sizeof(double), cudaMemcpyDefault) != cudaSuccess)
+                rc = cuda_fail(cudaGetLastError(), "cudaMemcpy(peer table)");
+    }
+    cudaFree(d_Ku);
+    return rc;
+}
+
+// finite-horizon LQR controller over a device-resident gain table [S][N-1][nu][n] (borrowed: the caller keeps it alive and frees it)
+int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev, const double* zd,
+                            const double* Fd, ccb_ctrl** out) {
+    if (!m || S < 1 || N < 2 || nu < 1 || !eqc || !K_dev || !zd || !Fd || !out) { set_error("ccb_lqr_ctrl_from_table: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_lqr_ctrl_from_table"));
+    CCB_TRY(check_device(device, "ccb_lqr_ctrl_from_table"));
+    const int nb = m->h.nb, n = 12 * nb;
+    ccb_ctrl* c = new ccb_ctrl();
+    c->device = device; c->B = S;
+    std::memset(&c->v, 0, sizeof(c->v));
+    c->v.nu = nu; c->v.kind = CCB_CTRL_LQR_FIN; c->v.N = N;
+    c->v.K = K_dev; c->v.K_bs = S > 1 ? (long long)(N - 1) * nu * n : 0;
+    auto fail = [&](int rc) { ccb_ctrl_destroy(c); return rc; };
     void *p_eqc = nullptr, *p_zd = nullptr, *p_Fd = nullptr;
     if (cudaMalloc(&p_eqc, nu * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
     c->allocs.push_back(p_eqc);

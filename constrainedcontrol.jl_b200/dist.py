@@ -43,3 +43,105 @@ def sharded_synthesis(synth_fn, total: int, device=None):
     else:
         lo, hi = 0, total
     return allgather_gains(synth_fn(lo, hi), total, device)
+
+
+class PeerGainTable:
+    """A device-resident table of finite-horizon LQR gains [S_total][N-1][nu][n] that the GPUs of a node fill TOGETHER: every rank
+    synthesises its shard of the systems and its Riccati sweep stores each gain row into every rank's table while it runs (peer
+    stores over NVLink through CUDA IPC mappings) -- the all-gather of SURVEY 8(e) fused into the kernel (ccb_lqr_synthesize_peers).
+    Without an initialised process group (or with one rank) it degenerates to a local synthesis into the rank's own table."""
+
+    def __init__(self, mech, zd_all, Fd_all, eqc_idx, Qd, Rd, N: int, device: int = 0, Q_batch=None, R_batch=None):
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, f64, i32, ptr
+        from .control import handle
+        import torch.distributed as dist
+        mh = handle(mech)
+        self.mech, self.device, self.N = mech, device, int(N)
+        eqc_idx = i32(eqc_idx); nu = eqc_idx.size
+        zd_all = f64(zd_all).reshape(-1, mh.nb, 13); S = zd_all.shape[0]
+        Fd_all = np.ascontiguousarray(np.broadcast_to(f64(Fd_all).reshape(-1, nu), (S, nu)))
+        self.S, self.nu, self.n = S, nu, mh.n
+        self.eqc_idx, self.zd_all, self.Fd_all = eqc_idx, zd_all, Fd_all
+        self.per = (self.N - 1) * nu * mh.n
+        L = _lib.lib()
+        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+        lo, hi = shard_range(S, rank, world)
+        self.shard = (lo, hi)
+        # my table + its IPC handle
+        self.ptr = C.c_void_p()
+        hbuf = (C.c_ubyte * 64)()
+        check(L.ccb_gains_alloc(C.c_int32(device), C.c_int64(S * self.per), C.byref(self.ptr), hbuf))
+        tables = [self.ptr]
+        opened = []
+        if active:
+            import torch
+            dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+            mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8, device=dev)
+            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            for r in range(world):
+                if r == rank:
+                    continue
+                hb = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                p = C.c_void_p()
+                check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(p)))
+                opened.append(p); tables.append(p)
+        # my shard, written into every table as the sweep produces it
+        Qd = f64(Qd); Rd = f64(Rd)
+        if Q_batch is not None:
+            Qs, qbs = np.ascontiguousarray(f64(Q_batch)[lo:hi]), mh.n * mh.n
+        else:
+            Qs, qbs = Qd, 0
+        if R_batch is not None:
+            Rs, rbs = np.ascontiguousarray(f64(R_batch)[lo:hi]), nu * nu
+        else:
+            Rs, rbs = Rd, 0
+        self.kexit = np.zeros(S, np.int32); self.iters = np.zeros(S, np.int32)
+        if hi > lo:
+            arr = (C.c_void_p * len(tables))(*[t.value for t in tables])
+            kx = np.empty(hi - lo, np.int32); it = np.empty(hi - lo, np.int32)
+            zl = np.ascontiguousarray(zd_all[lo:hi]); fl = np.ascontiguousarray(Fd_all[lo:hi])
+            check(L.ccb_lqr_synthesize_peers(mh.h, C.c_int32(device), C.c_int32(hi - lo), ptr(zl), ptr(fl), ptr(eqc_idx), C.c_int32(nu), ptr(Qs), C.c_int64(qbs),
+                                             ptr(Rs), C.c_int64(rbs), C.c_int32(self.N), None, C.c_int32(len(tables)), arr, C.c_int64(lo), ptr(kx), ptr(it)))
+            self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
+        if active:
+            import torch
+            if dist.get_backend() == "nccl":
+                torch.cuda.synchronize(device)
+            dist.barrier()                       # every rank's stores into my table have landed
+            for p in opened:
+                check(L.ccb_gains_close(p))
+        self._ctrl = None
+
+    def read(self, s0: int = 0, count: int = None) -> np.ndarray:
+        """gain tables of systems s0 .. s0+count-1 as a host array [count][N-1][nu][n]"""
+        import ctypes as C
+        from . import _lib
+        from ._lib import check, ptr
+        count = self.S - s0 if count is None else count
+        out = np.empty((count, self.N - 1, self.nu, self.n))
+        check(_lib.lib().ccb_gains_read(C.c_int32(self.device), self.ptr, C.c_int64(s0 * self.per), ptr(out), C.c_int64(count * self.per)))
+        return out
+
+    def controller(self):
+        """finite-horizon LQR controller (control_lqr!, lqr.jl:89-114) over the table, one gain table per system"""
+        from .control import TableLQR
+        if self._ctrl is None:
+            self._ctrl = TableLQR(self)
+        return self._ctrl
+
+    def free(self):
+        from . import _lib
+        if self._ctrl is not None:
+            self._ctrl.invalidate(); self._ctrl = None
+        if self.ptr:
+            _lib.lib().ccb_gains_free(self.ptr); self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -235,6 +235,27 @@ int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const
 int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m, const double* A, const double* B, const double* Q,
                   const double* R, double* X, double* K, int32_t* iters, int32_t* status);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: LQR syntheses sharded over the GPUs of a node, every GPU needing every gain table.  Instead of an
+ * all-gather after the fact, the Riccati sweep stores each gain row into every GPU's table while it runs (plain stores into peer
+ * memory over NVLink): a table is allocated on each rank (ccb_gains_alloc, which also returns its CUDA IPC handle), the 64-byte
+ * handles are exchanged by the host (torch.distributed / MPI / a Julia Channel), opened on the other ranks (ccb_gains_open), and
+ * ccb_lqr_synthesize_peers = ccb_lqr_synthesize with the gains of its S systems written at system index s_offset + s of every
+ * table in `tables` (1..8; the rank's own and the opened peers').  Tables are [S_total][N-1][nu][n].  The caller synchronises the
+ * ranks (a barrier) before anybody reads a table.  Shapes the tensor-core sweep K4 does not take are synthesised locally and copied
+ * to the tables.  ccb_lqr_ctrl_from_table builds a finite-horizon LQR controller (lqr.jl:89-114) on such a table (borrowed).
+ * ------------------------------------------------------------------------------------------------ */
+int ccb_gains_alloc(int32_t device, int64_t count, double** dptr, unsigned char ipc_handle[64]);
+int ccb_gains_open(int32_t device, const unsigned char ipc_handle[64], double** dptr);
+int ccb_gains_close(double* dptr);
+int ccb_gains_free(double* dptr);
+int ccb_gains_read(int32_t device, const double* dptr, int64_t offset, double* host, int64_t count);
+int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
+                             const double* Q, int64_t Q_bstride, const double* R, int64_t R_bstride, int32_t N, const ccb_sim_opts* opts,
+                             int32_t ntables, double* const* tables, int64_t s_offset, int32_t* kexit, int32_t* iters);
+int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev,
+                            const double* zd, const double* Fd, ccb_ctrl** out);
+
 /* The synthesis calls keep their device scratch (up to a quarter of the device memory; CCB_ARENA_MAX_GB overrides) between calls so
  * that repeated syntheses do not pay cudaMalloc / cudaFree again; this gives it back.  No reference counterpart (Julia's GC). */
 int ccb_scratch_release(void);

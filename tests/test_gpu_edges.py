@@ -109,3 +109,17 @@ def test_error_returns(cc, cartpole_setup):
     # no such device
     with pytest.raises(cc.CcbError, match="CUDA device"):
         cc.lqr_synthesize(mech, o["zd"][None], np.zeros((1, 1)), [0], np.eye(24), np.eye(1), 5, device=99)
+
+
+def test_peer_gain_tables_two_ranks(cc):
+    """2 GPUs: the Riccati sweep of each rank stores its gain rows into both ranks' tables (CUDA IPC, NVLink); tools/peer_check.py asserts
+    bit-identity with the NCCL all-gather and with a local synthesis.  Skipped on single-GPU boxes."""
+    import subprocess, sys, os
+    if cc.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(root, "tools", "peer_check.py"), "cartpole", "64", "300"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("table == gathered: True") == 2
