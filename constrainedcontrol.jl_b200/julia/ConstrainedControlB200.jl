@@ -352,4 +352,34 @@ dlqr(A, B, Q, R, Δt::Real; kw...) = dlqr(A .* Δt .+ Matrix{Float64}(I, size(A,
 "give the library's persistent device scratch (kept between synthesis calls) back to the driver"
 release_scratch() = check(ccall((:ccb_scratch_release, libccb), Cint, ()))
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# Multi-GPU (one Julia process per GPU, e.g. Distributed.jl workers): gain tables that every GPU of the node needs are filled by
+# the Riccati sweeps of all ranks together -- each rank's kernel stores its rows into every rank's table over NVLink (CUDA IPC).
+#   t, h = gains_alloc(count; device)            my table and its 64-byte IPC handle (send `h` to the other ranks)
+#   p = gains_open(h; device)                    map a peer's table
+#   synthesize_peers!(mh, zd, Fτd, eqcidx, Qd, Rd, N, tables, s_offset; device)   my shard -> all tables;  then a barrier
+# ---------------------------------------------------------------------------------------------------------------------------
+function gains_alloc(count::Integer; device = 0)
+    p = Ref{Ptr{Float64}}(C_NULL); h = zeros(UInt8, 64)
+    check(ccall((:ccb_gains_alloc, libccb), Cint, (Int32, Int64, Ref{Ptr{Float64}}, Ptr{UInt8}), device, count, p, h))
+    return p[], h
+end
+function gains_open(h::Vector{UInt8}; device = 0)
+    p = Ref{Ptr{Float64}}(C_NULL)
+    check(ccall((:ccb_gains_open, libccb), Cint, (Int32, Ptr{UInt8}, Ref{Ptr{Float64}}), device, h, p))
+    return p[]
+end
+gains_close(p::Ptr{Float64}) = check(ccall((:ccb_gains_close, libccb), Cint, (Ptr{Float64},), p))
+gains_free(p::Ptr{Float64}) = check(ccall((:ccb_gains_free, libccb), Cint, (Ptr{Float64},), p))
+function synthesize_peers!(mh::MechHandle, zd::Array{Float64,3}, Fτd::Matrix{Float64}, eqcidx::Vector{Int32}, Qd::Matrix{Float64}, Rd::Matrix{Float64},
+                           N::Integer, tables::Vector{Ptr{Float64}}, s_offset::Integer; device = 0)
+    S = size(zd, 3); nu = length(eqcidx)
+    kexit = zeros(Int32, S); iters = zeros(Int32, S)
+    check(ccall((:ccb_lqr_synthesize_peers, libccb), Cint,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int32, Ptr{Cvoid},
+                 Int32, Ptr{Ptr{Float64}}, Int64, Ptr{Int32}, Ptr{Int32}),
+                mh.ptr, device, S, zd, Fτd, eqcidx, nu, permutedims(Qd), 0, permutedims(Rd), 0, N, C_NULL, length(tables), tables, s_offset, kexit, iters))
+    return kexit, iters
+end
+
 end # module
