@@ -485,7 +485,8 @@ __global__ void step_major_kernel(const double* __restrict__ in, double* __restr
 
 static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const double* traj, const double* Ftau, const int32_t* eqc, int nu,
                                  const double* Q, const double* R, const ccb_sim_opts* opts, double* Ku_host, double* d_Ku_all,
-                                 double* d_traj_keep, double* d_F_keep, int32_t* kexit, int32_t* iters) {
+                                 double* d_traj_keep, double* d_F_keep, int32_t* kexit, int32_t* iters, int peer_copy_n = 0,
+                                 double* const* peer_copy_t = nullptr) {
     const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
     // every (trajectory, k) linearisation is independent (lqr_tracking.jl:88); only Pk carries the recursion.
     // Chunk over trajectories so that the per-chunk matrices use at most half of the free HBM (180 GB per B200), in equal chunks.
@@ -521,9 +522,12 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
     if (pipeline && !d_traj_keep) CCB_TRY(sc.get(&d_zs, P * nb * 13));
     if (pipeline && !d_F_keep) CCB_TRY(sc.get(&d_fs, P * nu));
     PhaseTimer pt;
+    const long long peer_off0 = g_peer_tables.s_offset;           // ccb_tracking_synthesize_peers: slot of trajectory 0 in the peer tables
+    struct PeerOffsetRestore { long long v; ~PeerOffsetRestore() { g_peer_tables.s_offset = v; } } peer_restore{peer_off0};
     for (int s0 = 0; s0 < S; s0 += chunk) {
         const int cs = std::min(chunk, S - s0);
         const int Pc = cs * N;
+        g_peer_tables.s_offset = peer_off0 + s0;
         double* Kdst = d_Ku_all ? d_Ku_all + (size_t)s0 * (N - 1) * nu * n : d_Ku;
         const double* h_traj = traj + (size_t)s0 * N * nb * 13;
         const double* h_F = Ftau + (size_t)s0 * N * nu;
@@ -605,6 +609,9 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
             cudaGetLastError();
             cleanup();
         }
+        if (peer_copy_n > 0)                                       // kernels that do not store into the peer tables themselves: copy the finished pass
+            for (int i = 0; i < peer_copy_n; i++)
+                CCB_CUDA(cudaMemcpy(peer_copy_t[i] + (size_t)(peer_off0 + s0) * (N - 1) * nu * n, Kdst, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDefault));
         if (Ku_host) CCB_CUDA(cudaMemcpy(Ku_host + (size_t)s0 * (N - 1) * nu * n, Kdst, (size_t)cs * (N - 1) * nu * n * sizeof(double), cudaMemcpyDeviceToHost));
         if (kexit) CCB_CUDA(cudaMemcpy(kexit + s0, d_kexit, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
         if (iters) CCB_CUDA(cudaMemcpy(iters + s0, d_iters, (size_t)cs * sizeof(int), cudaMemcpyDeviceToHost));
@@ -618,6 +625,26 @@ int ccb_tracking_synthesize(ccb_mech* m, int32_t device, int32_t S, int32_t N, c
     CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_synthesize"));
     CCB_TRY(check_device(device, "ccb_tracking_synthesize"));
     return tracking_synth_device(m, device, S, N, traj, Ftau, eqc, nu, Q, R, opts, Ku, nullptr, nullptr, nullptr, kexit, iters);
+}
+
+// ccb_tracking_synthesize with the gain tables of the S trajectories stored at index s_offset + s of every table (see ccb_lqr_synthesize_peers)
+int ccb_tracking_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
+                                  int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, int32_t ntables, double* const* tables,
+                                  int64_t s_offset, int32_t* kexit, int32_t* iters) {
+    if (!m || S < 1 || N < 2 || !traj || !Ftau || nu < 1 || !eqc || !Q || !R || ntables < 1 || ntables > 8 || !tables || s_offset < 0) {
+        set_error("ccb_tracking_synthesize_peers: bad arguments (1..8 tables)");
+        return CCB_E_INVALID;
+    }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_synthesize_peers"));
+    CCB_TRY(check_device(device, "ccb_tracking_synthesize_peers"));
+    const bool fused = riccati_dmma_eligible(12 * m->h.nb, nu) && !getenv("CCB_NO_DMMA");
+    g_peer_tables.n = fused ? ntables : 0;
+    g_peer_tables.s_offset = s_offset;
+    for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
+    const int rc = tracking_synth_device(m, device, S, N, traj, Ftau, eqc, nu, Q, R, opts, nullptr, nullptr, nullptr, nullptr, kexit, iters,
+                                         fused ? 0 : ntables, tables);
+    g_peer_tables.n = 0; g_peer_tables.s_offset = 0;
+    return rc;
 }
 
 int ccb_tracking_create(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc, int32_t nu,

@@ -243,7 +243,8 @@ int ccb_are_solve(int32_t device, int32_t kind, int32_t S, int32_t n, int32_t m,
  * ccb_lqr_synthesize_peers = ccb_lqr_synthesize with the gains of its S systems written at system index s_offset + s of every
  * table in `tables` (1..8; the rank's own and the opened peers').  Tables are [S_total][N-1][nu][n].  The caller synchronises the
  * ranks (a barrier) before anybody reads a table.  Shapes the tensor-core sweep K4 does not take are synthesised locally and copied
- * to the tables.  ccb_lqr_ctrl_from_table builds a finite-horizon LQR controller (lqr.jl:89-114) on such a table (borrowed).
+ * to the tables.  ccb_tracking_synthesize_peers is the same for ccb_tracking_synthesize (the SURVEY 8(e) case: 64 TrackingLQR tables of
+ * 9.4 MB each that all 8 GPUs need).  ccb_lqr_ctrl_from_table builds a finite-horizon LQR controller (lqr.jl:89-114) on such a table (borrowed).
  * ------------------------------------------------------------------------------------------------ */
 int ccb_gains_alloc(int32_t device, int64_t count, double** dptr, unsigned char ipc_handle[64]);
 int ccb_gains_open(int32_t device, const unsigned char ipc_handle[64], double** dptr);
@@ -253,6 +254,9 @@ int ccb_gains_read(int32_t device, const double* dptr, int64_t offset, double* h
 int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
                              const double* Q, int64_t Q_bstride, const double* R, int64_t R_bstride, int32_t N, const ccb_sim_opts* opts,
                              int32_t ntables, double* const* tables, int64_t s_offset, int32_t* kexit, int32_t* iters);
+int ccb_tracking_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, int32_t N, const double* traj, const double* Ftau, const int32_t* eqc,
+                                  int32_t nu, const double* Q, const double* R, const ccb_sim_opts* opts, int32_t ntables, double* const* tables,
+                                  int64_t s_offset, int32_t* kexit, int32_t* iters);
 int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev,
                             const double* zd, const double* Fd, ccb_ctrl** out);
 

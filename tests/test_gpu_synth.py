@@ -193,3 +193,36 @@ def test_peer_gain_table_single_rank_matches_synthesis_and_drives_a_rollout(cc, 
     # a shape outside the tensor-core sweep (n = 12 nb with nb = 9 -> 108 is K4; the double pendulum's n = 24 is too: use CCB_NO_DMMA elsewhere) --
     # here: the large-n path copies the finished shard instead
     tab.free()
+
+
+def test_tracking_synthesis_into_a_device_table(cc, orc):
+    """ccb_tracking_synthesize_peers with one table: the gain rows of the TrackingLQR sweep (pipelined over step blocks at this horizon) land in
+    the device-resident table at the given system offset, bit-identical to ccb_tracking_synthesize"""
+    import ctypes as C
+    from ccb200 import _lib
+    mech, cfg = cc.examples.triple_cartpole()
+    N = 300
+    U = np.load(__file__.replace("test_gpu_synth.py", "golden/triple_cartpole_U.npy"))[:N].reshape(N, 1)
+    ol = cc.OpenLoop(mech, cfg["eqcids"], U)
+    sto = cc.Storage(N, mech.nb)
+    cc.simulate(mech, sto, ol, record=True)
+    tl = cc.TrackingLQR(mech, sto, U.reshape(1, N, 1), cfg["eqcids"], cfg["Q"], cfg["R"])
+    Kref = tl.K[0]
+    n, nu = 12 * mech.nb, 1
+    per = (N - 1) * nu * n
+    L = _lib.lib()
+    tab = C.c_void_p()
+    _lib.check(L.ccb_gains_alloc(C.c_int32(0), C.c_int64(3 * per), C.byref(tab), None))
+    arr = (C.c_void_p * 1)(tab.value)
+    traj = np.ascontiguousarray(sto.data[:, 0]).reshape(1, N, mech.nb, 13)
+    Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
+    eqc = _lib.i32([mech.eqc_index(i) for i in cfg["eqcids"]])
+    kx = np.zeros(1, np.int32); it = np.zeros(1, np.int32)
+    Ft = np.ascontiguousarray(U.reshape(1, N, 1))
+    _lib.check(L.ccb_tracking_synthesize_peers(cc.handle(mech).h, C.c_int32(0), C.c_int32(1), C.c_int32(N), _lib.ptr(traj), _lib.ptr(Ft), _lib.ptr(eqc),
+                                              C.c_int32(nu), _lib.ptr(Qd), _lib.ptr(Rd), None, C.c_int32(1), arr, C.c_int64(2), _lib.ptr(kx), _lib.ptr(it)))
+    out = np.empty((N - 1, nu, n))
+    _lib.check(L.ccb_gains_read(C.c_int32(0), tab, C.c_int64(2 * per), _lib.ptr(out), C.c_int64(per)))
+    _lib.check(L.ccb_gains_free(tab))
+    assert kx[0] == tl.kexit[0]
+    assert np.array_equal(out, Kref)
