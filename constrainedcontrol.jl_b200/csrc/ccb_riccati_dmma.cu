@@ -67,6 +67,22 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     const double* Rg = R + s * R_bs;
     double* Kout = Ku + s * (size_t)(N - 1) * nu * n;
     const size_t kbase = (size_t)(peers.s_offset + (long long)s) * (size_t)(N - 1) * nu * n;      // my system's slot in the peer tables
+    // Peer tables (multi-GPU): the gain rows go to the local table as they are produced and are pushed to every peer table in
+    // contiguous runs of kPeerFlush rows (rows of consecutive steps are adjacent in [s][k][nu][n]): a few hundred KB of streaming 16-byte
+    // stores per peer every kPeerFlush iterations, hidden under the recursion.  (Row-by-row remote stores were 20x slower on 8 GPUs:
+    // 128 CTAs x 8 tables of ~10 GB touch more 2 MB pages than the TLB holds.)
+    constexpr int kPeerFlush = 64;
+    int flush_hi = k_hi;                                      // rows k-1 for k in (.., flush_hi] are not pushed yet
+    auto peer_flush = [&](int k_from) {                       // push rows (k_from - 1) .. (flush_hi - 1); all threads, after a barrier
+        if (peers.n == 0 || flush_hi < k_from) return;
+        const size_t off = (size_t)(k_from - 1) * nu * n, cnt2 = (size_t)(flush_hi - k_from + 1) * nu * n / 2;
+        const double2* src = reinterpret_cast<const double2*>(Kout + off);
+        for (int pt = 0; pt < peers.n; pt++) {
+            double2* dst = reinterpret_cast<double2*>(peers.t[pt] + kbase + off);
+            for (size_t e = tid; e < cnt2; e += NT) dst[e] = src[e];
+        }
+        flush_hi = k_from - 1;
+    };
     const int i0 = 8 * w;                                     // my strip
     const int ra = min(i0 + g, n - 1);                        // clamped row of my A fragments / C fragments
     const bool row_ok = i0 + g < n;
@@ -200,7 +216,6 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 const double x0 = Kk[c] * inv;
                 Kk[c] = x0;
                 Kout[(size_t)(k - 1) * n + c] = x0;                          // lqr.jl:162-164
-                for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k - 1) * n + c] = x0;      // ... and into the peer tables (NVLink stores)
                 RK[c] = r00 * x0;
             }
         } else {
@@ -233,10 +248,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     Kk[i * LD + c] = x[i];
-                    if (i < nu) {
-                        Kout[(size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];      // lqr.jl:162-164
-                        for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];
-                    }
+                    if (i < nu) Kout[(size_t)(k - 1) * nu * n + (size_t)i * n + c] = x[i];      // lqr.jl:162-164
                     double acc = 0.0;
 #pragma unroll
                     for (int j = 0; j < 8; j++) acc = fma(Rs[i * 8 + j], x[j], acc);
@@ -370,21 +382,20 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         }
         __syncthreads();
         if (brk) break;
+        if (flush_hi - k + 1 >= kPeerFlush) peer_flush(k);
     }
-    if (k < k_lo && k_lo > 1) {                                          // this launch's part is done, the sweep is not: park P for the next launch
+    if (k < k_lo && k_lo > 1) {
+        peer_flush(k_lo);                                          // this launch's part is done, the sweep is not: park P for the next launch
         for (size_t e = tid; e < nn; e += NT) { const int i = (int)(e / n), j = (int)(e % n); Pg[e] = Ps[(size_t)i * LD + j]; }
         if (tid == 0) { kexit[s] = 0; iters[s] = (resume ? iters[s] : 0) + it; }
         return;
     }
     if (k < 1) k = 1;                                                    // a completed loop leaves k == 1
     for (int k2 = k - 1; k2 >= 1; k2--) {                                // lqr.jl:179-181 back-fill
-        for (int e = tid; e < nu * n; e += NT) {
-            const double v = Kout[(size_t)k2 * nu * n + e];
-            Kout[(size_t)(k2 - 1) * nu * n + e] = v;
-            for (int pt = 0; pt < peers.n; pt++) peers.t[pt][kbase + (size_t)(k2 - 1) * nu * n + e] = v;
-        }
+        for (int e = tid; e < nu * n; e += NT) Kout[(size_t)(k2 - 1) * nu * n + e] = Kout[(size_t)k2 * nu * n + e];
         __syncthreads();
     }
+    peer_flush(1);                                                       // whatever is left, the back-filled rows included
     if (tid == 0) { kexit[s] = k; iters[s] = (resume ? iters[s] : 0) + it; }
 }
 
