@@ -70,6 +70,8 @@ class PeerGainTable:
         world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
         lo, hi = shard_range(S, rank, world)
         self.shard = (lo, hi)
+        import time
+        t_0 = time.time()
         # my table + its IPC handle
         self.ptr = C.c_void_p()
         hbuf = (C.c_ubyte * 64)()
@@ -89,6 +91,7 @@ class PeerGainTable:
                 p = C.c_void_p()
                 check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(p)))
                 opened.append(p); tables.append(p)
+        t_1 = time.time()
         # my shard, written into every table as the sweep produces it
         Qd = f64(Qd); Rd = f64(Rd)
         if Q_batch is not None:
@@ -107,6 +110,7 @@ class PeerGainTable:
             check(L.ccb_lqr_synthesize_peers(mh.h, C.c_int32(device), C.c_int32(hi - lo), ptr(zl), ptr(fl), ptr(eqc_idx), C.c_int32(nu), ptr(Qs), C.c_int64(qbs),
                                              ptr(Rs), C.c_int64(rbs), C.c_int32(self.N), None, C.c_int32(len(tables)), arr, C.c_int64(lo), ptr(kx), ptr(it)))
             self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
+        t_2 = time.time()
         if active:
             import torch
             if dist.get_backend() == "nccl":
@@ -114,6 +118,8 @@ class PeerGainTable:
             dist.barrier()                       # every rank's stores into my table have landed
             for p in opened:
                 check(L.ccb_gains_close(p))
+        # wall-clock split of the exchange: table allocation + handle exchange + IPC mapping | synthesis with the pushes | barrier + unmapping
+        self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
         self._ctrl = None
 
     def read(self, s0: int = 0, count: int = None) -> np.ndarray:

@@ -56,7 +56,7 @@ olo2 = olo; ohi2 = min(ohi, olo + 8)
 loc = cc.lqr_synthesize(mech, zd[olo2:ohi2], Fd[olo2:ohi2], eqc_idx, Qb[olo2:ohi2], Rb[olo2:ohi2], N, device=local)
 ok_local = np.array_equal(full[olo2:ohi2], loc["Ku"])
 print(f"rank {rank}/{world} {name} S={S} N={N}: fused-into-sweep {t_f*1e3:.1f} ms, synthesise + NCCL all-gather {t_g*1e3:.1f} ms; "
-      f"table == gathered: {ok_gather}; peer-written slice == local synthesis: {ok_local}", flush=True)
+      f"table == gathered: {ok_gather}; peer-written slice == local synthesis: {ok_local}; split {({k: round(v * 1e3, 1) for k, v in tab.timing.items()})} ms", flush=True)
 assert ok_gather and ok_local
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
