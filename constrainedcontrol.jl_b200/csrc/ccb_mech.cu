@@ -110,7 +110,19 @@ int build_host_mech(const ccb_mech_desc* d, HostMech* M) {
     for (int v = 1; v <= N; v++) std::sort(nbrs[v].begin(), nbrs[v].end());
     M->parents.assign(N, 0);
     std::vector<int> colour(N + 1, 0), cursor(N + 1, 0), stack;
-    for (int root = 1; root <= N; root++) {
+    // The origin is the root of the mechanism graph: the search starts at the equality constraints attached to it (ascending ids), whatever
+    // their position in the list; components without an origin joint follow in ascending id order (same rule as the oracle: bit-exact test).
+    std::vector<int> roots;
+    {
+        std::vector<char> at_origin(ne, 0);
+        for (int j = 0; j < nj; j++) if (M->j_parent[j] < 0) at_origin[M->j_eqc[j]] = 1;
+        std::vector<int> ids;
+        for (int e = 0; e < ne; e++) if (at_origin[e]) ids.push_back(M->eqc_id[e]);
+        std::sort(ids.begin(), ids.end());
+        roots = ids;
+        for (int v = 1; v <= N; v++) roots.push_back(v);
+    }
+    for (int root : roots) {
         if (colour[root]) continue;
         stack.push_back(root); colour[root] = 1;
         while (!stack.empty()) {

@@ -61,6 +61,10 @@ void build_graph(Mech& M) {
     M.parents.assign(N, 0);
     M.dfs_list.clear(); M.loop_edges.clear();
     std::vector<int> state(N, 0);
+    // The origin is the root of the mechanism graph: the depth-first search starts at the equality constraints attached to it (ascending
+    // ids), whatever their position in the list -- an origin joint with a single body must not end up as a LEAF of the elimination tree
+    // (its diagonal block is zero until its body has been eliminated).  Components without an origin joint follow in ascending id order.
+    for (int v = 0; v < M.ne; v++) if (state[v] == 0 && M.eqc_parent[v] < 0) dfs_visit(v, -1, adj, state, M);
     for (int v = 0; v < N; v++) if (state[v] == 0) dfs_visit(v, -1, adj, state, M);
 
     // block dims / offsets (dense KKT layout: bodies first, then lambda in eqc order)

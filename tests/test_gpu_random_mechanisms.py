@@ -137,3 +137,18 @@ def test_random_branching_tree_with_mixed_joint_dimensions(cc, orc, seed):
         sto, fin, status = cc.simulate(mech, 0.5, None, record=True, states=st0, lanes=lanes, return_status=True)
         assert np.all(status > 0), lanes
         assert rel_err(sto.data, r["storage"]) < TOL, lanes
+
+
+@pytest.mark.parametrize("order", [[0, 1, 2], [2, 0, 1], [1, 2, 0], [0, 2, 1]])
+def test_constraint_listing_order_does_not_change_the_trajectory(cc, orc, order):
+    """the same cart + double pendulum with its equality constraints listed in every order (ids, DFS order and the elimination order change):
+    every rollout kernel reproduces the trajectory of the canonical listing"""
+    from test_oracle_invariance import _chain
+    base = _chain(cc, [0, 1, 2])
+    ref = orc.OracleMech(base.desc()).simulate(base.state_vector()[None], 150, record=True)
+    mech = _chain(cc, order)
+    st0 = mech.state_vector()[None].copy()
+    for lanes in (0, 5, 6, 1, 32):
+        sto, fin, status = cc.simulate(mech, 1.5, None, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        assert rel_err(sto.data, ref["storage"]) < 1e-9, lanes
