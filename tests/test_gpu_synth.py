@@ -226,3 +226,19 @@ def test_tracking_synthesis_into_a_device_table(cc, orc):
     _lib.check(L.ccb_gains_free(tab))
     assert kx[0] == tl.kexit[0]
     assert np.array_equal(out, Kref)
+
+
+@pytest.mark.parametrize("n", [10, 24, 132])
+def test_gains_invariant_under_constraint_basis_and_multiplier_scaling_on_the_device(cc, n):
+    """SURVEY 8(c) item 9 on the product (K3 / K4 / K4b): Ku does not depend on the basis of the constraint rows or the scaling of the multipliers"""
+    rng = np.random.default_rng(n)
+    mu, ml, N = 2, 5, 30
+    A = rng.normal(size=(n, n)) * (0.8 / np.sqrt(n))
+    Bu = rng.normal(size=(n, mu)); Bl = rng.normal(size=(n, ml)); G = rng.normal(size=(ml, n))
+    Q = np.eye(n) * 0.02; R = np.eye(mu) * 0.05
+    T = rng.normal(size=(ml, ml)) + 3 * np.eye(ml)
+    Sc = np.diag(10.0 ** rng.uniform(-2, 2, ml)) @ (rng.normal(size=(ml, ml)) + 3 * np.eye(ml))
+    a = cc.dlqr(A[None], Bu[None], Bl[None], G[None], Q, R, N)
+    b = cc.dlqr(A[None], Bu[None], (Bl @ Sc)[None], (T @ G)[None], Q, R, N)
+    assert a["kexit"][0] == b["kexit"][0]
+    assert rel_err(b["Ku"][0], a["Ku"][0]) < 1e-9
