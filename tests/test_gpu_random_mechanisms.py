@@ -152,3 +152,19 @@ def test_constraint_listing_order_does_not_change_the_trajectory(cc, orc, order)
         sto, fin, status = cc.simulate(mech, 1.5, None, record=True, states=st0, lanes=lanes, return_status=True)
         assert np.all(status > 0), lanes
         assert rel_err(sto.data, ref["storage"]) < 1e-9, lanes
+
+
+@pytest.mark.parametrize("body_order,order", [((2, 0, 1), [0, 1, 2]), ((1, 2, 0), [2, 1, 0])])
+def test_body_listing_order_does_not_change_the_motion(cc, orc, body_order, order):
+    """bodies (and constraints) listed in another order: the state array is permuted, the motion of each named body is not -- every kernel"""
+    from test_oracle_invariance import _chain
+    base = _chain(cc, [0, 1, 2])
+    ref = orc.OracleMech(base.desc()).simulate(base.state_vector()[None], 150, record=True)["storage"][:, 0]
+    ref_by_name = {b.name: ref[:, i] for i, b in enumerate(base.bodies)}
+    mech = _chain(cc, order, body_order)
+    st0 = mech.state_vector()[None].copy()
+    for lanes in (0, 6, 1, 32):
+        sto, fin, status = cc.simulate(mech, 1.5, None, record=True, states=st0, lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        for i, b in enumerate(mech.bodies):
+            assert rel_err(sto.data[:, 0, i], ref_by_name[b.name]) < 1e-9, (lanes, b.name)

@@ -21,8 +21,8 @@ def test_gains_are_invariant_under_constraint_basis_and_multiplier_scaling(orc):
     assert np.abs(np.asarray(out["Ku"]) - np.asarray(ref["Ku"])).max() < 1e-10 * np.abs(np.asarray(ref["Ku"])).max()
 
 
-def _chain(cc, order):
-    """cart + two pendulum links; `order` permutes the list of equality constraints handed to Mechanism"""
+def _chain(cc, order, body_order=(0, 1, 2)):
+    """cart + two pendulum links; `order` permutes the list of equality constraints handed to Mechanism, `body_order` the list of bodies"""
     from ccb200 import Box, EqualityConstraint, Mechanism, Origin, Prismatic, Revolute, RotX, setPosition
     EX, EY = np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0])
     p = np.array([0.0, 0.0, 0.5])
@@ -33,7 +33,8 @@ def _chain(cc, order):
     j1 = EqualityConstraint(Revolute(cart, l1, EX, p2=-p), name="j1")
     j2 = EqualityConstraint(Revolute(l1, l2, EX, p1=p, p2=-p), name="j2")
     eqcs = [j0, j1, j2]
-    mech = Mechanism(origin, [cart, l1, l2], [eqcs[i] for i in order], g=-9.81, dt=0.01)
+    bodies = [cart, l1, l2]
+    mech = Mechanism(origin, [bodies[i] for i in body_order], [eqcs[i] for i in order], g=-9.81, dt=0.01)
     setPosition(origin, cart, dx=[0.0, 0.1, 0.0])
     setPosition(cart, l1, p2=-p, dq=RotX(math.pi - 0.3))
     setPosition(l1, l2, p1=p, p2=-p, dq=RotX(0.4))
@@ -51,3 +52,18 @@ def test_states_are_invariant_under_the_order_of_the_equality_constraints(cc, or
     assert not np.array_equal(runs[0][0]["dfs_list"], runs[1][0]["dfs_list"])      # the orderings really differ ...
     for g, sto in runs[1:]:
         assert np.abs(sto - runs[0][1]).max() < 1e-9                                # ... the trajectory (a swinging double pendulum on a cart) does not
+
+
+def test_states_are_invariant_under_the_order_of_the_bodies(cc, orc):
+    """listing the bodies in another order permutes the state array (and the columns of A, K) but not the motion of each body"""
+    ref = None
+    for body_order, order in (((0, 1, 2), [0, 1, 2]), ((2, 0, 1), [0, 1, 2]), ((1, 2, 0), [2, 1, 0])):
+        mech = _chain(cc, order, body_order)
+        om = orc.OracleMech(mech.desc())
+        r = om.simulate(mech.state_vector()[None], 200, record=True)
+        assert r["iters"][0] > 0
+        by_name = {b.name: r["storage"][:, 0, i] for i, b in enumerate(mech.bodies)}
+        if ref is None:
+            ref = by_name
+        for name in ref:
+            assert np.abs(by_name[name] - ref[name]).max() < 1e-9, (body_order, name)
