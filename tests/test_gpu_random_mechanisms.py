@@ -202,3 +202,43 @@ def test_lqr_closed_loop_is_invariant_under_listing_orders(cc):
             assert np.abs(by_name["cart"][-1, 1]) < 0.05           # the controller does bring the cart back
         for name in ref:
             assert rel_err(by_name[name], ref[name]) < 1e-7, (body_order, order, name)
+
+
+def test_two_independent_pendulums_in_one_mechanism(cc, orc):
+    """a forest: two pendulums that share nothing but the origin, as ONE mechanism (two components, two origin joints).  Each must move exactly
+    like the single pendulum -- exercises the component handling of the graph code and of the kernel choice (this is not a serial chain)"""
+    import math
+    from ccb200 import Box, EqualityConstraint, Mechanism, Origin, Revolute, RotX, setPosition
+    EX = np.array([1.0, 0.0, 0.0])
+    p = np.array([0.0, 0.0, 0.5])
+
+    def build(angles):
+        origin = Origin()
+        bodies, eqcs = [], []
+        for i, a in enumerate(angles):
+            b = Box(0.1, 0.1, 1.0, 1.0 + 0.5 * i, name=f"b{i}")
+            eqcs.append(EqualityConstraint(Revolute(origin, b, EX, p2=-p), name=f"j{i}"))
+            bodies.append(b)
+        mech = Mechanism(origin, bodies, eqcs, g=-9.81, dt=0.01)
+        for b, a in zip(bodies, angles):
+            setPosition(origin, b, p2=-p, dq=RotX(a))
+        return mech
+
+    both = build([0.7, -1.1])
+    singles = [build([0.7]), None]
+    # the second pendulum alone (heavier box): build it as the only body of its own mechanism
+    origin = Origin()
+    b1 = Box(0.1, 0.1, 1.0, 1.5, name="b1")
+    m1 = Mechanism(origin, [b1], [EqualityConstraint(Revolute(origin, b1, EX, p2=-p), name="j1")], g=-9.81, dt=0.01)
+    setPosition(origin, b1, p2=-p, dq=RotX(-1.1))
+    singles[1] = m1
+    refs = [orc.OracleMech(m.desc()).simulate(m.state_vector()[None], 200, record=True)["storage"][:, 0, 0] for m in singles]
+    ob = orc.OracleMech(both.desc()).simulate(both.state_vector()[None], 200, record=True)
+    assert ob["iters"][0] > 0
+    for i in range(2):
+        assert rel_err(ob["storage"][:, 0, i], refs[i]) < 1e-9
+    for lanes in (0, 8, 32):
+        sto, fin, status = cc.simulate(both, 2.0, None, record=True, states=both.state_vector()[None].copy(), lanes=lanes, return_status=True)
+        assert np.all(status > 0), lanes
+        for i in range(2):
+            assert rel_err(sto.data[:, 0, i], refs[i]) < 1e-9, (lanes, i)
