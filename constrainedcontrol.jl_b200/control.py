@@ -232,6 +232,33 @@ class TableLQR(Controller):
         self._h = {}
 
 
+class TableTracking(TableLQR):
+    """TrackingLQR (control_trackinglqr!, lqr_tracking.jl:46-71) over a device-resident gain table filled by dist.PeerTrackingTable"""
+
+    kind = CTRL_TRACKING
+
+    def device_handle(self, B: int, device: int):
+        t = self.table
+        per = getattr(self, "_per_table", 1)
+        if B != t.S * per or device != t.device:
+            raise CcbError(f"TableTracking: the table holds {t.S} trajectories (x {per} systems each) on device {t.device}")
+        if device not in self._h:
+            h = C.c_void_p()
+            check(_lib.lib().ccb_tracking_ctrl_from_table(handle(self.mech).h, C.c_int32(device), C.c_int32(t.S), C.c_int32(t.N), C.c_int32(t.nu), ptr(t.eqc_idx),
+                                                         t.ptr, ptr(t.traj), ptr(t.Ftau), C.byref(h)))
+            self._h[device] = h
+            if per > 1:
+                check(_lib.lib().ccb_ctrl_set_replication(h, C.c_int32(per)))
+        return self._h[device]
+
+    def replicate(self, per_table: int):
+        """let `per_table` consecutive systems of the batch share one trajectory's tables"""
+        self._per_table = int(per_table)
+        for h in self._h.values():
+            check(_lib.lib().ccb_ctrl_set_replication(h, C.c_int32(per_table)))
+        return self
+
+
 def _stride(a: np.ndarray, per: int, B: int) -> int:
     if a.size == per:
         return 0

@@ -459,6 +459,38 @@ int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, i
     return CCB_OK;
 }
 
+// TrackingLQR controller (control_trackinglqr!, lqr_tracking.jl:46-71) over a device-resident gain table [S][N-1][nu][n] (borrowed), with the
+// desired trajectories [S][N][nb][13] and feed-forward inputs [S][N][nu] copied from the host
+int ccb_tracking_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev,
+                                 const double* traj, const double* Ftau, ccb_ctrl** out) {
+    if (!m || S < 1 || N < 2 || nu < 1 || !eqc || !K_dev || !traj || !Ftau || !out) { set_error("ccb_tracking_ctrl_from_table: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_eqcs(m->h, eqc, nu, "ccb_tracking_ctrl_from_table"));
+    CCB_TRY(check_device(device, "ccb_tracking_ctrl_from_table"));
+    const int nb = m->h.nb, n = 12 * nb;
+    ccb_ctrl* c = new ccb_ctrl();
+    c->device = device; c->B = S;
+    std::memset(&c->v, 0, sizeof(c->v));
+    c->v.nu = nu; c->v.kind = CCB_CTRL_TRACKING; c->v.N = N;
+    c->v.K = K_dev; c->v.K_bs = S > 1 ? (long long)(N - 1) * nu * n : 0;
+    auto fail = [&](int rc) { ccb_ctrl_destroy(c); return rc; };
+    void *p_eqc = nullptr, *p_zd = nullptr, *p_Fd = nullptr;
+    if (cudaMalloc(&p_eqc, nu * sizeof(int)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_eqc);
+    if (cudaMalloc(&p_zd, (size_t)S * N * nb * 13 * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_zd);
+    if (cudaMalloc(&p_Fd, (size_t)S * N * nu * sizeof(double)) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    c->allocs.push_back(p_Fd);
+    if (cudaMemcpy(p_eqc, eqc, nu * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_zd, traj, (size_t)S * N * nb * 13 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p_Fd, Ftau, (size_t)S * N * nu * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
+    c->v.eqc = (const int*)p_eqc;
+    c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)N * nb * 13 : 0;
+    c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)N * nu : 0;
+    *out = c;
+    return CCB_OK;
+}
+
 int ccb_ctrl_get_gains(ccb_ctrl* c, int32_t n, double* K, int64_t count) {
     if (!c || !K || !c->v.K) { set_error("ccb_ctrl_get_gains: controller has no gain table"); return CCB_E_INVALID; }
     const int64_t rows = c->v.kind == CCB_CTRL_LQR_INF ? 1 : (int64_t)c->v.N - 1;

@@ -151,3 +151,80 @@ class PeerGainTable:
             self.free()
         except Exception:
             pass
+
+
+class PeerTrackingTable:
+    """TrackingLQR gain tables [S_total][N-1][nu][n] of S_total reference trajectories (64 Sawyer tables of 9.4 MB that all
+    8 GPUs need) filled by the ranks together: every rank linearises and sweeps its shard of the trajectories and its Riccati kernel
+    pushes the gain rows into every rank's table (ccb_tracking_synthesize_peers).  Same protocol as PeerGainTable."""
+
+    def __init__(self, mech, storage, Ftau, eqcids, Q, R, device: int = 0):
+        import ctypes as C
+        import time
+        from . import _lib
+        from ._lib import check, f64, i32, ptr
+        from .control import blockdiag, handle
+        import torch.distributed as dist
+        mh = handle(mech)
+        self.mech, self.device = mech, device
+        traj = np.ascontiguousarray(np.swapaxes(f64(storage.data), 0, 1))          # [S][N][nb][13]
+        S, N = traj.shape[0], traj.shape[1]
+        eqc_idx = i32([mech.eqc_index(i) for i in eqcids]); nu = eqc_idx.size
+        Ftau = np.ascontiguousarray(np.broadcast_to(f64(Ftau).reshape(-1, N, nu), (S, N, nu)))
+        Qd = f64(blockdiag(Q) * mech.dt); Rd = f64(blockdiag(R) * mech.dt)       # lqr_tracking.jl:22-23
+        self.S, self.N, self.nu, self.n = S, N, nu, mh.n
+        self.eqc_idx, self.traj, self.Ftau = eqc_idx, traj, Ftau
+        self.per = (N - 1) * nu * mh.n
+        L = _lib.lib()
+        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+        lo, hi = shard_range(S, rank, world)
+        self.shard = (lo, hi)
+        t_0 = time.time()
+        self.ptr = C.c_void_p()
+        hbuf = (C.c_ubyte * 64)()
+        check(L.ccb_gains_alloc(C.c_int32(device), C.c_int64(S * self.per), C.byref(self.ptr), hbuf))
+        tables, opened = [self.ptr], []
+        if active:
+            import torch
+            dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+            mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8, device=dev)
+            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            for r in range(world):
+                if r == rank:
+                    continue
+                hb = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                p = C.c_void_p()
+                check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(p)))
+                opened.append(p); tables.append(p)
+        t_1 = time.time()
+        self.kexit = np.zeros(S, np.int32); self.iters = np.zeros(S, np.int32)
+        if hi > lo:
+            arr = (C.c_void_p * len(tables))(*[t.value for t in tables])
+            kx = np.empty(hi - lo, np.int32); it = np.empty(hi - lo, np.int32)
+            tl = np.ascontiguousarray(traj[lo:hi]); fl = np.ascontiguousarray(Ftau[lo:hi])
+            check(L.ccb_tracking_synthesize_peers(mh.h, C.c_int32(device), C.c_int32(hi - lo), C.c_int32(N), ptr(tl), ptr(fl), ptr(eqc_idx), C.c_int32(nu),
+                                                  ptr(Qd), ptr(Rd), None, C.c_int32(len(tables)), arr, C.c_int64(lo), ptr(kx), ptr(it)))
+            self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
+        t_2 = time.time()
+        if active:
+            import torch
+            if dist.get_backend() == "nccl":
+                torch.cuda.synchronize(device)
+            dist.barrier()
+            for p in opened:
+                check(L.ccb_gains_close(p))
+        self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
+        self._ctrl = None
+
+    read = PeerGainTable.read
+    free = PeerGainTable.free
+    __del__ = PeerGainTable.__del__
+
+    def controller(self):
+        """TrackingLQR controller (control_trackinglqr!, lqr_tracking.jl:46-71) over the table, one table per reference trajectory"""
+        from .control import TableTracking
+        if self._ctrl is None:
+            self._ctrl = TableTracking(self)
+        return self._ctrl

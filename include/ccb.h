@@ -259,6 +259,9 @@ int ccb_tracking_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, int32_
                                   int64_t s_offset, int32_t* kexit, int32_t* iters);
 int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev,
                             const double* zd, const double* Fd, ccb_ctrl** out);
+/* the same for control_trackinglqr! (lqr_tracking.jl:46-71): traj [S][N][nb][13], Ftau [S][N][nu] are copied, the gain table is borrowed */
+int ccb_tracking_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, int32_t nu, const int32_t* eqc, const double* K_dev,
+                                 const double* traj, const double* Ftau, ccb_ctrl** out);
 
 /* The synthesis calls keep their device scratch (up to a quarter of the device memory; CCB_ARENA_MAX_GB overrides) between calls so
  * that repeated syntheses do not pay cudaMalloc / cudaFree again; this gives it back.  No reference counterpart (Julia's GC). */

@@ -242,3 +242,25 @@ def test_gains_invariant_under_constraint_basis_and_multiplier_scaling_on_the_de
     b = cc.dlqr(A[None], Bu[None], (Bl @ Sc)[None], (T @ G)[None], Q, R, N)
     assert a["kexit"][0] == b["kexit"][0]
     assert rel_err(b["Ku"][0], a["Ku"][0]) < 1e-9
+
+
+def test_peer_tracking_table_matches_tracking_lqr(cc):
+    """dist.PeerTrackingTable (single rank here): the TrackingLQR gain tables of 3 reference trajectories in a device-resident table, and a
+    controller over it (2 perturbed systems per trajectory) -- bit-identical to TrackingLQR + replicate"""
+    mech, cfg = cc.examples.triple_cartpole()
+    N, S, PER = 200, 3, 2
+    U0 = np.load(__file__.replace("test_gpu_synth.py", "golden/triple_cartpole_U.npy"))[:N]
+    U = np.stack([U0 * sc for sc in (1.0, 0.8, 1.1)]).reshape(S, N, 1)
+    st0 = mech.batch_states(S)
+    ol = cc.OpenLoop(mech, cfg["eqcids"], U)
+    sto, fin, status = cc.simulate(mech, N * mech.dt, ol, record=True, states=st0, return_status=True)
+    assert np.all(status > 0)
+    tl = cc.TrackingLQR(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"])
+    tab = cc.dist.PeerTrackingTable(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"])
+    assert np.array_equal(tab.read(), tl.K) and np.array_equal(tab.kexit, tl.kexit)
+    stp = np.repeat(st0, PER, axis=0); stp[:, 0, 1] += np.linspace(-0.01, 0.01, S * PER)
+    a = cc.simulate(mech, N * mech.dt, tl.replicate(PER), record=False, states=stp)
+    b = cc.simulate(mech, N * mech.dt, tab.controller().replicate(PER), record=False, states=stp)
+    fa = a[1] if isinstance(a, tuple) else a; fb = b[1] if isinstance(b, tuple) else b
+    assert np.array_equal(fa, fb)
+    tab.free()
