@@ -45,6 +45,16 @@ def sharded_synthesis(synth_fn, total: int, device=None):
     return allgather_gains(synth_fn(lo, hi), total, device)
 
 
+def _share_counters(tab, dist, device):
+    """exit indices / iteration counts of every shard on every rank (each rank filled only its own slice: a sum gathers them)"""
+    import torch
+    dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(np.stack([tab.kexit, tab.iters]).astype(np.int64)).to(dev)
+    dist.all_reduce(t)
+    t = t.cpu().numpy()
+    tab.kexit, tab.iters = t[0].astype(np.int32), t[1].astype(np.int32)
+
+
 class PeerGainTable:
     """A device-resident table of finite-horizon LQR gains [S_total][N-1][nu][n] that the GPUs of a node fill TOGETHER: every rank
     synthesises its shard of the systems and its Riccati sweep stores each gain row into every rank's table while it runs (peer
@@ -118,6 +128,7 @@ class PeerGainTable:
             dist.barrier()                       # every rank's stores into my table have landed
             for p in opened:
                 check(L.ccb_gains_close(p))
+            _share_counters(self, dist, device)
         # wall-clock split of the exchange: table allocation + handle exchange + IPC mapping | synthesis with the pushes | barrier + unmapping
         self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
         self._ctrl = None
@@ -215,6 +226,7 @@ class PeerTrackingTable:
             dist.barrier()
             for p in opened:
                 check(L.ccb_gains_close(p))
+            _share_counters(self, dist, device)
         self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
         self._ctrl = None
 
