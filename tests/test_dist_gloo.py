@@ -38,6 +38,40 @@ def _worker(rank, world, port, total, q):
     dist.destroy_process_group()
 
 
+def _worker_counters(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ccb200 as cc
+
+    class Tab:      # the counters of a peer gain table: every rank has filled its own slice only
+        pass
+    t = Tab()
+    lo, hi = cc.dist.shard_range(total, rank, world)
+    t.kexit = np.zeros(total, np.int32); t.iters = np.zeros(total, np.int32)
+    t.kexit[lo:hi] = np.arange(lo, hi) + 1; t.iters[lo:hi] = 100 + np.arange(lo, hi)
+    cc.dist._share_counters(t, dist, 0)
+    ok = np.array_equal(t.kexit, np.arange(total) + 1) and np.array_equal(t.iters, 100 + np.arange(total)) and t.kexit.dtype == np.int32
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_peer_table_counters_are_shared_world2():
+    """host half of the fused multi-GPU gain exchange (dist.PeerGainTable): exit indices and iteration counts of every shard reach every rank"""
+    world, total = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_counters, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]
+
+
 @pytest.mark.parametrize("total", [7, 8])
 def test_shard_and_allgather_gains_world2(total):
     world = 2
