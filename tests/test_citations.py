@@ -11,8 +11,15 @@ KNOWN = {"lqr.jl": "src/control/lqr.jl", "lqr_tracking.jl": "src/control/lqr_tra
          "ConstrainedControl.jl": "src/ConstrainedControl.jl", "Project.toml": "Project.toml", "README.md": "README.md"}
 
 
+import glob
+
+DOCS = ["include/ccb.h", "DESIGN.md", "INTEGRATION.md"] + sorted(
+    os.path.relpath(f, ROOT) for pat in ("constrainedcontrol.jl_b200/csrc/*.cu", "constrainedcontrol.jl_b200/csrc/*.cuh", "constrainedcontrol.jl_b200/*.py",
+                                          "oracle/*.cpp", "oracle/*.hpp", "oracle/*.py") for f in glob.glob(os.path.join(ROOT, pat)))
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
-@pytest.mark.parametrize("doc", ["include/ccb.h", "DESIGN.md", "INTEGRATION.md"])
+@pytest.mark.parametrize("doc", DOCS)
 def test_reference_citations_resolve(doc):
     text = open(os.path.join(ROOT, doc)).read()
     checked = 0
@@ -32,4 +39,4 @@ def test_reference_citations_resolve(doc):
         n = sum(1 for _ in open(f, errors="replace"))
         assert 1 <= line <= n, f"{doc}: {path}:{line} is beyond the file's {n} lines"
         checked += 1
-    assert checked > 5
+    assert checked > 5 or doc not in ("include/ccb.h", "DESIGN.md", "INTEGRATION.md")
