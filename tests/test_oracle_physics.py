@@ -102,3 +102,23 @@ def test_graph_orderings(cc, orc):
     g = orc.OracleMech(mech.desc()).graph()
     assert len(g["loop_edges"]) == 2
     assert sorted(g["dfs_list"].tolist()) == list(range(1, 11))
+
+
+def test_integrator_is_first_order_accurate(cc, orc):
+    """the reference's variational integrator is first order (README.md:14 paper): halving the step halves the error of a pendulum swing
+    against a fine-step run of the same restatement"""
+    import math
+    T = 1.0
+
+    def angle_at_T(dt):
+        mech, _ = cc.examples.pendulum(phi0=0.5, dt=dt)
+        om = orc.OracleMech(mech.desc())
+        r = om.simulate(mech.state_vector()[None], int(round(T / dt)), record=False)
+        assert r["iters"][0] > 0
+        q = r["states"][0, 0, 3:7]
+        return 2 * math.atan2(q[1], q[0])
+
+    ref = angle_at_T(0.00025)
+    e1, e2 = abs(angle_at_T(0.01) - ref), abs(angle_at_T(0.005) - ref)
+    assert 1e-6 < e2 < e1 < 5e-2
+    assert 1.6 < e1 / e2 < 2.5, e1 / e2
