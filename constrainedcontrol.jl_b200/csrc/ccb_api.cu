@@ -8,6 +8,16 @@ const char* last_error_cstr();
 }
 using namespace ccb;
 
+namespace ccb {
+// Uploads and memsets of the create functions run on the legacy default stream; batch streams are non-blocking and therefore NOT ordered
+// against it (and a cudaMemcpy from pageable memory may return before its DMA has landed).  Every create function ends with this, so a
+// rollout launched on a batch stream right after it sees the finished tables.
+int finish_uploads() {
+    CCB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    return CCB_OK;
+}
+}  // namespace ccb
+
 extern "C" {
 
 const char* ccb_last_error(void) { return last_error_cstr(); }
@@ -58,14 +68,17 @@ int ccb_batch_create(ccb_mech* m, int32_t B, int32_t device, ccb_batch** out) {
     const DevMech* view;
     int rc = get_dev_mech(&m->h, device, &view);
     if (rc != CCB_OK) return rc;
+    CCB_CUDA(cudaSetDevice(device));
     ccb_batch* b = new ccb_batch();
     b->mech = m; b->B = B; b->device = device;
-    CCB_CUDA(cudaSetDevice(device));
-    CCB_CUDA(cudaMalloc(&b->state, (size_t)B * m->h.nb * 13 * sizeof(double)));
-    CCB_CUDA(cudaMalloc(&b->lambda, (size_t)B * (m->h.ml > 0 ? m->h.ml : 1) * sizeof(double)));
-    CCB_CUDA(cudaMalloc(&b->status_dev, (size_t)B * sizeof(int)));
-    CCB_CUDA(cudaMemset(b->lambda, 0, (size_t)B * (m->h.ml > 0 ? m->h.ml : 1) * sizeof(double)));
-    CCB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    const size_t nl = (size_t)B * (m->h.ml > 0 ? m->h.ml : 1) * sizeof(double);
+    cudaError_t e = cudaMalloc(&b->state, (size_t)B * m->h.nb * 13 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->lambda, nl);
+    if (e == cudaSuccess) e = cudaMalloc(&b->status_dev, (size_t)B * sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->lambda, 0, nl, b->stream);     // on the consuming stream
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { ccb_batch_destroy(b); return cuda_fail(e, "ccb_batch_create"); }
     *out = b;
     return CCB_OK;
 }
@@ -128,6 +141,20 @@ static int upload(ccb_ctrl* c, const void* host, size_t bytes, const void** dev)
     return CCB_OK;
 }
 
+// integrator / last-error state of a PID controller for `B` systems (pid.jl:5-6), zeroed; replaces an earlier allocation
+static int pid_state_alloc(ccb_ctrl* c, int B) {
+    const size_t bytes = (size_t)B * c->v.nu * sizeof(double);
+    for (double** slot : {&c->v.pid_int, &c->v.pid_last}) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(PID state)");
+        c->allocs.push_back(q);
+        *slot = (double*)q;
+        if ((e = cudaMemset(q, 0, bytes)) != cudaSuccess) return cuda_fail(e, "cudaMemset(PID state)");
+    }
+    return CCB_OK;
+}
+
 int ccb_ctrl_create(const ccb_mech* m, const ccb_ctrl_desc* d, int32_t device, ccb_ctrl** out) {
     if (!m || !d || !out) { set_error("ccb_ctrl_create: NULL"); return CCB_E_INVALID; }
     if (ccb_device_count() <= device || device < 0) { set_error("ccb_ctrl_create: no such CUDA device (this library has no CPU fallback)"); return CCB_E_CUDA; }
@@ -174,12 +201,9 @@ int ccb_ctrl_create(const ccb_mech* m, const ccb_ctrl_desc* d, int32_t device, c
         if ((rc = upload(c, d->D, nu * sizeof(double), &p))) return fail(rc); c->v.D = (const double*)p;
         if ((rc = upload(c, d->goal, mult(d->goal_bstride) * nu * sizeof(double), &p))) return fail(rc);
         c->v.goal = (const double*)p; c->v.goal_bs = d->goal_bstride;
-        void* q = nullptr;
-        CCB_CUDA(cudaMalloc(&q, (size_t)B * nu * sizeof(double))); c->allocs.push_back(q); c->v.pid_int = (double*)q;
-        CCB_CUDA(cudaMemset(q, 0, (size_t)B * nu * sizeof(double)));
-        CCB_CUDA(cudaMalloc(&q, (size_t)B * nu * sizeof(double))); c->allocs.push_back(q); c->v.pid_last = (double*)q;
-        CCB_CUDA(cudaMemset(q, 0, (size_t)B * nu * sizeof(double)));
+        if ((rc = pid_state_alloc(c, B))) return fail(rc);
     }
+    if ((rc = finish_uploads())) return fail(rc);
     *out = c;
     return CCB_OK;
 }
@@ -205,6 +229,7 @@ int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t se
     if (set) {
         if (integrated) CCB_CUDA(cudaMemcpy(c->v.pid_int, integrated, bytes, cudaMemcpyHostToDevice));
         if (last) CCB_CUDA(cudaMemcpy(c->v.pid_last, last, bytes, cudaMemcpyHostToDevice));
+        return finish_uploads();
     } else {
         if (integrated) CCB_CUDA(cudaMemcpy(integrated, c->v.pid_int, bytes, cudaMemcpyDeviceToHost));
         if (last) CCB_CUDA(cudaMemcpy(last, c->v.pid_last, bytes, cudaMemcpyDeviceToHost));
@@ -217,10 +242,21 @@ int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps,
                         int32_t* status_dev) {
     if (!b || steps < 0) { set_error("ccb_simulate: bad arguments"); return CCB_E_INVALID; }
     if (ctrl && ctrl->device != b->device) { set_error("ccb_simulate: controller lives on another device"); return CCB_E_INVALID; }
-    if (ctrl && ctrl->B != 1 && (long long)ctrl->B * (ctrl->v.sys_div > 1 ? ctrl->v.sys_div : 1) != b->B) {
-        set_error("ccb_simulate: controller tables were laid out for another batch size"); return CCB_E_INVALID;
-    }
     CCB_CUDA(cudaSetDevice(b->device));
+    if (ctrl && (long long)ctrl->B * (ctrl->v.sys_div > 1 ? ctrl->v.sys_div : 1) != b->B) {
+        // a controller laid out for another batch size is only usable when NOTHING in it is indexed by the system: every per-system
+        // stride zero (one shared table / goal).  PID additionally carries per-system integrator state [B][nu] (pid.jl:5-6): a shared-goal
+        // PID built for one system is re-sized to this batch (state reset), anything else is refused.
+        const DevCtrl& v = ctrl->v;
+        const bool shared = v.K_bs == 0 && v.zd_bs == 0 && v.Fd_bs == 0 && v.U_bs == 0 && v.goal_bs == 0 && v.sys_div <= 1;
+        if (!shared || ctrl->B != 1) { set_error("ccb_simulate: controller tables were laid out for another batch size"); return CCB_E_INVALID; }
+        if (v.kind == CCB_CTRL_PID) {
+            int rc0 = pid_state_alloc(ctrl, b->B);
+            if (rc0 != CCB_OK) return rc0;
+            ctrl->B = b->B;
+            if ((rc0 = finish_uploads()) != CCB_OK) return rc0;
+        }
+    }
     const DevMech* view;
     int rc = get_dev_mech(&b->mech->h, b->device, &view);
     if (rc != CCB_OK) return rc;
@@ -245,7 +281,8 @@ int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const 
         const size_t need = per_step * steps * sizeof(double);
         if (b->storage_cap < need) {
             cudaFree(b->storage_dev); b->storage_dev = nullptr; b->storage_cap = 0;
-            CCB_CUDA(cudaMalloc(&b->storage_dev, need));
+            cudaError_t e = cudaMalloc(&b->storage_dev, need);
+            if (e != cudaSuccess) { b->storage_dev = nullptr; return cuda_fail(e, "cudaMalloc(storage)"); }
             b->storage_cap = need;
         }
         sdev = b->storage_dev;

@@ -18,6 +18,7 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 extern int64_t g_launches;
+int finish_uploads();   // ccb_api.cu: legacy-stream uploads of a create function have landed (batch streams are non-blocking)
 
 // ---------------------------------------------------------------------------------------------
 // Flattened, device-resident description of one mechanism + the symbolic plan of its Schur sweep.

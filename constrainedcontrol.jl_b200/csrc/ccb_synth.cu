@@ -102,6 +102,29 @@ struct PhaseTimer {
     }
 };
 
+// every linearisation rests on one Newton solve of its knot (lambda_d, v2, w2): a knot whose solve did not converge would silently turn
+// into garbage A, B, G and gains, so the synthesis entry points fail instead (status <= 0 marks a failed solve, ccb_simulate's convention)
+__global__ void count_failed_kernel(const int* __restrict__ status, int count, int* __restrict__ out) {
+    int bad = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) bad += status[i] <= 0;
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
+}
+int check_knot_status(const int* d_status, int count, int* d_counter, const char* who) {
+    if (cudaMemset(d_counter, 0, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMemset");
+    count_failed_kernel<<<std::min(148, (count + 255) / 256), 256>>>(d_status, count, d_counter);
+    g_launches++;
+    int bad = 0;
+    cudaError_t e = cudaMemcpy(&bad, d_counter, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(knot status)");
+    if (bad) {
+        set_error(std::string(who) + ": linearsystem: the Newton solve of " + std::to_string(bad) + " of " + std::to_string(count) +
+                  " setpoints / trajectory knots did not converge (not an equilibrium within newton_iter iterations?)");
+        return CCB_E_INVALID;
+    }
+    return CCB_OK;
+}
+
 int check_device(int device, const char* who) {
     int nd = 0;
     if (cudaGetDeviceCount(&nd) != cudaSuccess || device < 0 || device >= nd) {
@@ -137,10 +160,11 @@ int ccb_linearize(ccb_mech* m, int32_t device, int32_t S, const double* zd, cons
     CCB_TRY(sc.put(&d_eqc, (const int*)eqc, (size_t)nu));
     CCB_TRY(sc.get(&d_A, (size_t)S * n * n)); CCB_TRY(sc.get(&d_Bu, (size_t)S * n * nu)); CCB_TRY(sc.get(&d_Bl, (size_t)S * n * ml));
     CCB_TRY(sc.get(&d_G, (size_t)S * ml * n)); CCB_TRY(sc.get(&d_lam, (size_t)S * ml)); CCB_TRY(sc.get(&d_s, (size_t)S * nb * 6));
-    CCB_TRY(sc.get(&d_status, (size_t)S));
+    CCB_TRY(sc.get(&d_status, (size_t)S)); int* d_cnt; CCB_TRY(sc.get(&d_cnt, (size_t)1));
     CCB_CUDA(cudaMemset(d_lam, 0, std::max<size_t>((size_t)S * ml, 1) * sizeof(double)));
     CCB_TRY(linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
     CCB_CUDA(cudaDeviceSynchronize());
+    CCB_TRY(check_knot_status(d_status, S, d_cnt, "ccb_linearize"));
     if (A) CCB_CUDA(cudaMemcpy(A, d_A, (size_t)S * n * n * sizeof(double), cudaMemcpyDeviceToHost));
     if (Bu && nu) CCB_CUDA(cudaMemcpy(Bu, d_Bu, (size_t)S * n * nu * sizeof(double), cudaMemcpyDeviceToHost));
     if (Bl && ml) CCB_CUDA(cudaMemcpy(Bl, d_Bl, (size_t)S * n * ml * sizeof(double), cudaMemcpyDeviceToHost));
@@ -240,6 +264,7 @@ static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, co
     CCB_TRY(sc.get(&d_ws1, (size_t)S * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)S * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)S)); CCB_TRY(sc.get(&d_iters, (size_t)S));
+    int* d_cnt; CCB_TRY(sc.get(&d_cnt, (size_t)1));
     double* d_Ku = nullptr;
     CCB_CUDA(cudaMalloc(&d_Ku, (size_t)S * (N - 1) * nu * n * sizeof(double)));
     auto bail = [&](int rc) { cudaFree(d_Ku); return rc; };
@@ -257,6 +282,7 @@ static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, co
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaDeviceSynchronize"));
     pt.finish(false);
+    if ((rc = check_knot_status(d_status, S, d_cnt, "LQR synthesis")) != CCB_OK) return bail(rc);
     if (kexit && cudaMemcpy(kexit, d_kexit, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
     if (iters && cudaMemcpy(iters, d_iters, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return bail(cuda_fail(cudaGetLastError(), "cudaMemcpy"));
     *d_Ku_out = d_Ku;
@@ -347,6 +373,7 @@ int ccb_lqr_create(ccb_mech* m, int32_t device, int32_t S, const double* zd, con
     c->v.eqc = (const int*)p_eqc;
     c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)nb * 13 : 0;
     c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)nu : 0;
+    { int rcu = finish_uploads(); if (rcu != CCB_OK) return fail(rcu); }
     *out = c;
     return CCB_OK;
 }
@@ -455,6 +482,7 @@ int ccb_lqr_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t N, i
     c->v.eqc = (const int*)p_eqc;
     c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)nb * 13 : 0;
     c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)nu : 0;
+    { int rcu = finish_uploads(); if (rcu != CCB_OK) return fail(rcu); }
     *out = c;
     return CCB_OK;
 }
@@ -487,6 +515,7 @@ int ccb_tracking_ctrl_from_table(ccb_mech* m, int32_t device, int32_t S, int32_t
     c->v.eqc = (const int*)p_eqc;
     c->v.zd = (const double*)p_zd; c->v.zd_bs = S > 1 ? (long long)N * nb * 13 : 0;
     c->v.Fd = (const double*)p_Fd; c->v.Fd_bs = S > 1 ? (long long)N * nu : 0;
+    { int rcu = finish_uploads(); if (rcu != CCB_OK) return fail(rcu); }
     *out = c;
     return CCB_OK;
 }
@@ -543,6 +572,7 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
     CCB_TRY(sc.get(&d_ws1, P * riccati_project_ws_doubles(n, nu, ml)));
     CCB_TRY(sc.get(&d_ws2, (size_t)chunk * riccati_sweep_ws_doubles(n, nu)));
     CCB_TRY(sc.get(&d_kexit, (size_t)chunk)); CCB_TRY(sc.get(&d_iters, (size_t)chunk));
+    int* d_cnt; CCB_TRY(sc.get(&d_cnt, (size_t)1));
     // k-pipeline (K4 sizes): the sweep consumes the linearisations from k = N-1 downwards and needs ~1 CTA per trajectory, so the
     // linearisation + projection of the next block of steps runs on a second stream while the sweep works through the previous one
     // (stream-ordered through events; the sweep is launched once per block and carries P through the global workspace).
@@ -580,6 +610,7 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
             CCB_CUDA(cudaDeviceSynchronize());
             pt.finish(s0 > 0);
             if (s0 == 0) g_phase_ms[3] = 0.0;
+            CCB_TRY(check_knot_status(d_status, Pc, d_cnt, "TrackingLQR synthesis"));
         } else {
             // step-major copies: row k of trajectory s goes to p = k * cs + s (contiguous upload, transposed on the device)
             const double* src_z = d_traj_keep ? d_traj_keep + (size_t)s0 * N * nb * 13 : nullptr;
@@ -640,6 +671,7 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
             g_phase_ms[3] = (s0 > 0 ? g_phase_ms[3] : 0.0) + total;
             cudaGetLastError();
             cleanup();
+            CCB_TRY(check_knot_status(d_status, E * cs, d_cnt, "TrackingLQR synthesis"));      // step-major: entries 0 .. N-2 of every trajectory
         }
         if (peer_copy_n > 0)                                       // kernels that do not store into the peer tables themselves: copy the finished pass
             for (int i = 0; i < peer_copy_n; i++)

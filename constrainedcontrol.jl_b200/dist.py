@@ -55,6 +55,98 @@ def _share_counters(tab, dist, device):
     tab.kexit, tab.iters = t[0].astype(np.int32), t[1].astype(np.int32)
 
 
+class PeerProtocolError(RuntimeError):
+    """a rank failed inside the peer-table protocol; every rank raises (none is left waiting at a barrier)"""
+
+
+def _peer_fill(tab, device: int, count: int, run_shard):
+    """The peer-table protocol shared by PeerGainTable and PeerTrackingTable:
+
+        1. every rank allocates its full table (`count` doubles) and publishes the CUDA IPC handle (+ an ok byte);
+        2. the peers' tables are mapped;
+        3. `run_shard(tables)` synthesises this rank's shard, its Riccati kernel storing the gain rows into every table;
+        4. an all-reduced ok flag and a barrier (every rank's stores into my table have landed), then the mappings are closed.
+
+    A failure on one rank (allocation, mapping, a synthesis error) is carried to step 4 instead of raised on the spot: the collective
+    calls are executed by every rank in the same order whatever happened locally, the opened mappings are always closed, the local
+    table is freed only AFTER the barrier (peers may still be storing into it), and then every rank raises PeerProtocolError."""
+    import ctypes as C
+    import time
+    from . import _lib
+    from ._lib import check
+    import torch.distributed as dist
+    L = _lib.lib()
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+    err = None
+    t_0 = time.time()
+    tab.ptr = C.c_void_p()
+    hbuf = (C.c_ubyte * 64)()
+    try:
+        check(L.ccb_gains_alloc(C.c_int32(device), C.c_int64(count), C.byref(tab.ptr), hbuf))
+    except Exception as e:          # noqa: BLE001 -- carried to the agreement below
+        err = e
+        tab.ptr = None
+    tables = [tab.ptr]
+    opened = []
+    peers_ok = True
+    if active:
+        import torch
+        dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(bytes(hbuf)) + [0 if err else 1], dtype=torch.uint8, device=dev)
+        allh = [torch.empty(65, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        allh = [h.cpu().tolist() for h in allh]
+        peers_ok = all(h[64] == 1 for h in allh)
+        if peers_ok:
+            try:
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    hb = (C.c_ubyte * 64)(*allh[r][:64])
+                    q = C.c_void_p()
+                    check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(q)))
+                    opened.append(q); tables.append(q)
+            except Exception as e:  # noqa: BLE001
+                err = e
+    t_1 = time.time()
+    try:
+        if err is None and peers_ok:
+            try:
+                run_shard(tables)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        t_2 = time.time()
+        all_ok = err is None and peers_ok
+        if active:
+            import torch
+            dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+            if dist.get_backend() == "nccl":
+                torch.cuda.synchronize(device)
+            flag = torch.tensor([1 if all_ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            all_ok = bool(int(flag.item()))
+            dist.barrier()                       # every rank's stores into my table have landed
+    finally:
+        for q in opened:
+            L.ccb_gains_close(q)
+    if not all_ok:
+        if tab.ptr:
+            L.ccb_gains_free(tab.ptr); tab.ptr = None
+        raise PeerProtocolError(f"peer gain-table exchange failed on rank {rank}: {err!r}" if err is not None
+                                else "peer gain-table exchange failed on another rank") from err
+    if active:
+        _share_counters(tab, dist, device)
+    # wall-clock split of the exchange: table allocation + handle exchange + IPC mapping | synthesis with the pushes | barrier + unmapping
+    tab.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
+
+
+def _world():
+    import torch.distributed as dist
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+
+
 class PeerGainTable:
     """A device-resident table of finite-horizon LQR gains [S_total][N-1][nu][n] that the GPUs of a node fill TOGETHER: every rank
     synthesises its shard of the systems and its Riccati sweep stores each gain row into every rank's table while it runs (peer
@@ -66,9 +158,9 @@ class PeerGainTable:
         from . import _lib
         from ._lib import check, f64, i32, ptr
         from .control import handle
-        import torch.distributed as dist
         mh = handle(mech)
         self.mech, self.device, self.N = mech, device, int(N)
+        self._ctrl, self.ptr = None, None
         eqc_idx = i32(eqc_idx); nu = eqc_idx.size
         zd_all = f64(zd_all).reshape(-1, mh.nb, 13); S = zd_all.shape[0]
         Fd_all = np.ascontiguousarray(np.broadcast_to(f64(Fd_all).reshape(-1, nu), (S, nu)))
@@ -76,33 +168,9 @@ class PeerGainTable:
         self.eqc_idx, self.zd_all, self.Fd_all = eqc_idx, zd_all, Fd_all
         self.per = (self.N - 1) * nu * mh.n
         L = _lib.lib()
-        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+        world, rank = _world()
         lo, hi = shard_range(S, rank, world)
         self.shard = (lo, hi)
-        import time
-        t_0 = time.time()
-        # my table + its IPC handle
-        self.ptr = C.c_void_p()
-        hbuf = (C.c_ubyte * 64)()
-        check(L.ccb_gains_alloc(C.c_int32(device), C.c_int64(S * self.per), C.byref(self.ptr), hbuf))
-        tables = [self.ptr]
-        opened = []
-        if active:
-            import torch
-            dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
-            mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8, device=dev)
-            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            for r in range(world):
-                if r == rank:
-                    continue
-                hb = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
-                p = C.c_void_p()
-                check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(p)))
-                opened.append(p); tables.append(p)
-        t_1 = time.time()
-        # my shard, written into every table as the sweep produces it
         Qd = f64(Qd); Rd = f64(Rd)
         if Q_batch is not None:
             Qs, qbs = np.ascontiguousarray(f64(Q_batch)[lo:hi]), mh.n * mh.n
@@ -113,25 +181,18 @@ class PeerGainTable:
         else:
             Rs, rbs = Rd, 0
         self.kexit = np.zeros(S, np.int32); self.iters = np.zeros(S, np.int32)
-        if hi > lo:
+
+        def run_shard(tables):      # my shard, written into every table as the sweep produces it
+            if hi <= lo:
+                return
             arr = (C.c_void_p * len(tables))(*[t.value for t in tables])
             kx = np.empty(hi - lo, np.int32); it = np.empty(hi - lo, np.int32)
             zl = np.ascontiguousarray(zd_all[lo:hi]); fl = np.ascontiguousarray(Fd_all[lo:hi])
             check(L.ccb_lqr_synthesize_peers(mh.h, C.c_int32(device), C.c_int32(hi - lo), ptr(zl), ptr(fl), ptr(eqc_idx), C.c_int32(nu), ptr(Qs), C.c_int64(qbs),
                                              ptr(Rs), C.c_int64(rbs), C.c_int32(self.N), None, C.c_int32(len(tables)), arr, C.c_int64(lo), ptr(kx), ptr(it)))
             self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
-        t_2 = time.time()
-        if active:
-            import torch
-            if dist.get_backend() == "nccl":
-                torch.cuda.synchronize(device)
-            dist.barrier()                       # every rank's stores into my table have landed
-            for p in opened:
-                check(L.ccb_gains_close(p))
-            _share_counters(self, dist, device)
-        # wall-clock split of the exchange: table allocation + handle exchange + IPC mapping | synthesis with the pushes | barrier + unmapping
-        self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
-        self._ctrl = None
+
+        _peer_fill(self, device, S * self.per, run_shard)
 
     def read(self, s0: int = 0, count: int = None) -> np.ndarray:
         """gain tables of systems s0 .. s0+count-1 as a host array [count][N-1][nu][n]"""
@@ -152,9 +213,9 @@ class PeerGainTable:
 
     def free(self):
         from . import _lib
-        if self._ctrl is not None:
+        if getattr(self, "_ctrl", None) is not None:
             self._ctrl.invalidate(); self._ctrl = None
-        if self.ptr:
+        if getattr(self, "ptr", None):
             _lib.lib().ccb_gains_free(self.ptr); self.ptr = None
 
     def __del__(self):
@@ -167,17 +228,16 @@ class PeerGainTable:
 class PeerTrackingTable:
     """TrackingLQR gain tables [S_total][N-1][nu][n] of S_total reference trajectories (64 Sawyer tables of 9.4 MB that all
     8 GPUs need) filled by the ranks together: every rank linearises and sweeps its shard of the trajectories and its Riccati kernel
-    pushes the gain rows into every rank's table (ccb_tracking_synthesize_peers).  Same protocol as PeerGainTable."""
+    pushes the gain rows into every rank's table (ccb_tracking_synthesize_peers).  Same protocol as PeerGainTable (_peer_fill)."""
 
     def __init__(self, mech, storage, Ftau, eqcids, Q, R, device: int = 0):
         import ctypes as C
-        import time
         from . import _lib
         from ._lib import check, f64, i32, ptr
         from .control import blockdiag, handle
-        import torch.distributed as dist
         mh = handle(mech)
         self.mech, self.device = mech, device
+        self._ctrl, self.ptr = None, None
         traj = np.ascontiguousarray(np.swapaxes(f64(storage.data), 0, 1))          # [S][N][nb][13]
         S, N = traj.shape[0], traj.shape[1]
         eqc_idx = i32([mech.eqc_index(i) for i in eqcids]); nu = eqc_idx.size
@@ -187,48 +247,22 @@ class PeerTrackingTable:
         self.eqc_idx, self.traj, self.Ftau = eqc_idx, traj, Ftau
         self.per = (N - 1) * nu * mh.n
         L = _lib.lib()
-        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        world, rank = (dist.get_world_size(), dist.get_rank()) if active else (1, 0)
+        world, rank = _world()
         lo, hi = shard_range(S, rank, world)
         self.shard = (lo, hi)
-        t_0 = time.time()
-        self.ptr = C.c_void_p()
-        hbuf = (C.c_ubyte * 64)()
-        check(L.ccb_gains_alloc(C.c_int32(device), C.c_int64(S * self.per), C.byref(self.ptr), hbuf))
-        tables, opened = [self.ptr], []
-        if active:
-            import torch
-            dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
-            mine = torch.tensor(list(bytes(hbuf)), dtype=torch.uint8, device=dev)
-            allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            for r in range(world):
-                if r == rank:
-                    continue
-                hb = (C.c_ubyte * 64)(*allh[r].cpu().tolist())
-                p = C.c_void_p()
-                check(L.ccb_gains_open(C.c_int32(device), hb, C.byref(p)))
-                opened.append(p); tables.append(p)
-        t_1 = time.time()
         self.kexit = np.zeros(S, np.int32); self.iters = np.zeros(S, np.int32)
-        if hi > lo:
+
+        def run_shard(tables):
+            if hi <= lo:
+                return
             arr = (C.c_void_p * len(tables))(*[t.value for t in tables])
             kx = np.empty(hi - lo, np.int32); it = np.empty(hi - lo, np.int32)
             tl = np.ascontiguousarray(traj[lo:hi]); fl = np.ascontiguousarray(Ftau[lo:hi])
             check(L.ccb_tracking_synthesize_peers(mh.h, C.c_int32(device), C.c_int32(hi - lo), C.c_int32(N), ptr(tl), ptr(fl), ptr(eqc_idx), C.c_int32(nu),
                                                   ptr(Qd), ptr(Rd), None, C.c_int32(len(tables)), arr, C.c_int64(lo), ptr(kx), ptr(it)))
             self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
-        t_2 = time.time()
-        if active:
-            import torch
-            if dist.get_backend() == "nccl":
-                torch.cuda.synchronize(device)
-            dist.barrier()
-            for p in opened:
-                check(L.ccb_gains_close(p))
-            _share_counters(self, dist, device)
-        self.timing = {"alloc_map_s": t_1 - t_0, "synthesis_s": t_2 - t_1, "barrier_unmap_s": time.time() - t_2}
-        self._ctrl = None
+
+        _peer_fill(self, device, S * self.per, run_shard)
 
     read = PeerGainTable.read
     free = PeerGainTable.free

@@ -47,6 +47,12 @@ def are_solve(kind, A, B, Q, R, want_X=True, want_K=False, device: int = 0, info
     out = [x[0] if single else x for x in (X, K) if x is not None]
     if info:
         out.append({"iters": iters, "status": status})
+    elif np.any(status != 0):
+        # the reference would return garbage or throw from ordschur (util.jl:15-18, :28-36); without info=True the caller cannot see the
+        # per-problem flags, so an unsolved problem must not pass silently
+        bad = np.flatnonzero(status != 0)
+        raise ArithmeticError(f"are_solve: {bad.size} of {S} problems have no stabilising solution within the doubling iteration "
+                              f"(first: problem {int(bad[0])}, status {int(status[bad[0]])}); pass info=True to get the per-problem flags")
     return out[0] if len(out) == 1 else tuple(out)
 
 

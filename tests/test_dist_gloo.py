@@ -57,6 +57,81 @@ def _worker_counters(rank, world, port, total, q):
     dist.destroy_process_group()
 
 
+class _StubLib:
+    """stands in for libccb.so in the protocol test: table handles are fake, nothing is computed"""
+
+    def __init__(self, log):
+        self.log = log
+
+    def ccb_gains_alloc(self, device, count, pptr, hbuf):
+        pptr._obj.value = 0x1000
+        self.log.append("alloc")
+        return 0
+
+    def ccb_gains_open(self, device, hb, pptr):
+        pptr._obj.value = 0x2000
+        self.log.append("open")
+        return 0
+
+    def ccb_gains_close(self, p):
+        self.log.append("close")
+        return 0
+
+    def ccb_gains_free(self, p):
+        self.log.append("free")
+        return 0
+
+
+def _worker_peer_failure(rank, world, port, fail_rank, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ccb200 as cc
+    log = []
+    cc._lib._LIB = _StubLib(log)
+
+    class Tab:
+        pass
+    t = Tab()
+    t.kexit = np.zeros(4, np.int32); t.iters = np.zeros(4, np.int32)
+
+    def run_shard(tables):
+        log.append(f"shard:{len(tables)}")
+        if rank == fail_rank:
+            raise RuntimeError("synthesis failed on this rank")
+
+    try:
+        cc.dist._peer_fill(t, 0, 128, run_shard)
+        outcome = "ok"
+    except cc.dist.PeerProtocolError as e:
+        outcome = "local" if "synthesis failed" in str(e) else "peer"
+    q.put((rank, outcome, list(log), t.ptr is None))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_peer_protocol_failure_reaches_every_rank_world2(fail_rank):
+    """a rank that fails inside the peer-table protocol must not leave the others at the barrier: every rank raises,
+    the mappings are closed and the local table is freed only after the barrier"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_peer_failure, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    if fail_rank < 0:
+        assert [r[1] for r in res] == ["ok", "ok"]
+        assert all(r[2] == ["alloc", "open", "shard:2", "close"] and not r[3] for r in res)
+    else:
+        assert [r[1] for r in res] == ["peer", "local"]
+        assert all(r[2] == ["alloc", "open", "shard:2", "close", "free"] and r[3] for r in res)
+
+
 def test_peer_table_counters_are_shared_world2():
     """host half of the fused multi-GPU gain exchange (dist.PeerGainTable): exit indices and iteration counts of every shard reach every rank"""
     world, total = 2, 7

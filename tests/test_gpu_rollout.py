@@ -111,3 +111,40 @@ def test_open_loop_table_and_recording(cc, orc):
     assert out is storage
     assert rel_err(storage.data, ref["storage"]) < TOL
     assert np.array_equal(storage.x[0][0], st0[0, 0, 0:3])   # Storage[1] is the initial continuous state
+
+
+def test_shared_goal_pid_built_for_one_system_runs_a_batch(cc, orc):
+    """ADVICE r1 (ccb_api.cu): the Julia shim's BatchPID with goals (nu,1) creates the controller with B = 1 / goal_bstride = 0 and then
+    simulates a larger batch.  The per-system integrator state must be re-sized to the batch (it used to be indexed out of bounds); a
+    controller with per-system tables laid out for another batch size must be refused."""
+    import ctypes as C
+    from ccb200 import _lib
+    mech, cfg = cc.examples.doublependulum()
+    B = 37
+    rng = np.random.default_rng(4)
+    st0 = mech.batch_states(B)
+    st0[:, :, 10] = rng.uniform(-0.5, 0.5, (B, mech.nb))          # distinct initial angular velocities
+    goal = np.array([[0.7, -0.4]])
+    pid = cc.PID(mech, cfg["eqcids"], goal, P=cfg["P"], I=cfg["I"], D=cfg["D"])
+    h1 = pid.device_handle(1, 0)                                   # built for ONE system: d.B = 1, goal_bstride = 0
+    batch = cc.Batch(mech, B, 0)
+    batch.set_state(st0)
+    opts = _lib.SimOpts(1e-10, 100, 10, 0, 0)
+    status = np.zeros(B, np.int32)
+    _lib.check(_lib.lib().ccb_simulate(batch.h, h1, C.c_int32(1), C.c_int32(150), C.byref(opts), None, _lib.ptr(status)))
+    final = batch.get_state()
+    om = orc.OracleMech(mech.desc())
+    eqc = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    integ = np.zeros((B, 2)); last = np.zeros((B, 2))
+    ctrl_o = om.make_ctrl(B, kind="pid", eqc=eqc, P=cfg["P"], I=cfg["I"], D=cfg["D"], goal=np.repeat(goal, B, axis=0), pid_int=integ, pid_last=last)
+    ref = om.simulate(st0, 150, ctrl=ctrl_o)
+    assert np.all(status > 0)
+    assert rel_err(final, ref["states"]) < TOL
+    gi, gl = np.zeros((B, 2)), np.zeros((B, 2))
+    _lib.check(_lib.lib().ccb_ctrl_pid_state(h1, _lib.ptr(gi), _lib.ptr(gl), C.c_int32(0)))       # now sized for the batch
+    assert rel_err(gi, integ) < TOL and rel_err(gl, last) < TOL
+    # per-system goals laid out for 5 systems on a batch of 37: refused
+    pid5 = cc.PID(mech, cfg["eqcids"], np.tile(goal, (5, 1)) + np.arange(5)[:, None] * 0.01, P=cfg["P"], I=cfg["I"], D=cfg["D"])
+    h5 = pid5.device_handle(5, 0)
+    rc = _lib.lib().ccb_simulate(batch.h, h5, C.c_int32(1), C.c_int32(1), C.byref(opts), None, None)
+    assert rc != 0 and b"another batch size" in _lib.lib().ccb_last_error()
