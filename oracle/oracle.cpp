@@ -579,13 +579,16 @@ int linearize(const Mech& M, Work& W, const double* zd, const double* Fd, const 
 // constrained Riccati step shared by lqr.jl:150-177 and lqr_tracking.jl:87-115 (identical text there)
 // Returns true when the early-break test `norm(Pk - Pkp1) < 1e-5` fires.  Writes Ku row block [mu][n].
 // ---------------------------------------------------------------------------------------------
-struct RicWork {
-    Mat GBl, GBlT, X, XG, D, DtP, M, b, Abar, t1, t2, P1, GBu, PA;
+template <class T> struct RicWorkT {
+    std::vector<T> GBl, GBlT, X, XG, D, DtP, M, b, Abar, t1, t2, P1, GBu, PA;
     std::vector<int> piv;
 };
+typedef RicWorkT<double> RicWork;
 
-bool riccati_step(const double* A, const double* Bu, const double* Bl, const double* G, const double* Q, const double* R, int n, int mu,
-                  int ml, Mat& P, double* Kuk_out, RicWork& w, double* normdiff) {
+template <class T>
+bool riccati_step(const T* A, const T* Bu, const T* Bl, const T* G, const T* Q, const T* R, int n, int mu,
+                  int ml, std::vector<T>& P, T* Kuk_out, RicWorkT<T>& w, T* normdiff) {
+    typedef std::vector<T> Mat;
     const int q = mu + ml;
     w.GBl.resize((size_t)ml * ml); w.GBlT.resize((size_t)ml * ml); w.X.resize((size_t)n * ml); w.XG.resize((size_t)n * n);
     w.D.resize((size_t)n * mu); w.DtP.resize((size_t)mu * n); w.M.resize((size_t)q * q); w.b.resize((size_t)q * n);
@@ -627,7 +630,7 @@ bool riccati_step(const double* A, const double* Bu, const double* Bl, const dou
     // Kk = M \ b                                                lqr.jl:160
     lu_factor(w.M.data(), q, w.piv.data());
     lu_solve(w.M.data(), w.piv.data(), q, w.b.data(), n);
-    const double* Kk = w.b.data();
+    const T* Kk = w.b.data();
     for (int i = 0; i < mu * n; i++) Kuk_out[i] = Kk[i];        // lqr.jl:162-164
     // Abar = A - Bu Kuk - Bl Klk                                lqr.jl:169
     mm(Bu, Kk, w.t1.data(), n, mu, n);
@@ -639,20 +642,48 @@ bool riccati_step(const double* A, const double* Bu, const double* Bl, const dou
     mtm(Kk, RK.data(), KRK.data(), n, mu, n);
     mtm(w.Abar.data(), P.data(), w.t1.data(), n, n, n);         // Abar' P
     mm(w.t1.data(), w.Abar.data(), w.t2.data(), n, n, n);
-    double nd = 0;
+    T nd = 0;
     for (int i = 0; i < n * n; i++) {
         w.P1[i] = Q[i] + KRK[i] + w.t2[i];
-        double d = P[i] - w.P1[i];
+        T d = P[i] - w.P1[i];
         nd += d * d;
     }
-    nd = std::sqrt(nd);
+    nd = t_sqrt(nd);
     *normdiff = nd;
-    if (nd < 1e-5) return true;                                  // lqr.jl:172 (Pk is NOT updated on break)
+    if (nd < T(1e-5)) return true;                                  // lqr.jl:172 (Pk is NOT updated on break)
     P = w.P1;
     return false;
 }
 
 }  // namespace
+
+// The same loop (lqr.jl:141-184) with the recursion carried in a wider scalar: prec 0 = Float64 (identical to orc_dlqr), 1 = x87 extended
+// (long double), 2 = IEEE binary128 (__float128).  Inputs and outputs are Float64 (the linearisation is the reference's Float64 data; gains are
+// rounded on output).  normdiff_trace [N-1] (optional) receives ||Pk - Pkp1||_F of every executed iteration -- the quantity the early break
+// of lqr.jl:172 compares with 1e-5.  Pmax_out (optional): max |P_ij| at exit.  Purpose: separating "two Float64 implementations differ" from
+// "the recursion amplifies rounding" (tests/test_oracle_quad.py, tools/quad_gains.py); never a parity reference by itself.
+template <class T>
+int dlqr_mp(const double* A_, const double* Bu_, const double* Bl_, const double* G_, const double* Q_, const double* R_, int n, int mu, int ml,
+                   int N, double* Ku, int* iters_out, double* normdiff_trace, double* Pmax_out) {
+    auto up = [](const double* p, size_t cnt) { std::vector<T> v(cnt); for (size_t i = 0; i < cnt; i++) v[i] = (T)p[i]; return v; };
+    std::vector<T> A = up(A_, (size_t)n * n), Bu = up(Bu_, (size_t)n * mu), Bl = up(Bl_, (size_t)n * ml), G = up(G_, (size_t)ml * n),
+                   Q = up(Q_, (size_t)n * n), R = up(R_, (size_t)mu * mu), P = Q, Kk((size_t)mu * n);
+    RicWorkT<T> w;
+    int k = 0, iters = 0;
+    T nd;
+    for (k = N - 1; k >= 1; k--) {
+        bool brk = riccati_step<T>(A.data(), Bu.data(), Bl.data(), G.data(), Q.data(), R.data(), n, mu, ml, P, Kk.data(), w, &nd);
+        for (int i = 0; i < mu * n; i++) Ku[(size_t)(k - 1) * mu * n + i] = (double)Kk[i];
+        if (normdiff_trace) normdiff_trace[iters] = (double)nd;
+        iters++;
+        if (brk) break;
+    }
+    if (k < 1) k = 1;
+    for (int k2 = k - 1; k2 >= 1; k2--) std::memcpy(Ku + (size_t)(k2 - 1) * mu * n, Ku + (size_t)k2 * mu * n, sizeof(double) * mu * n);
+    if (iters_out) *iters_out = iters;
+    if (Pmax_out) { T m = 0; for (auto& v : P) if (t_abs(v) > m) m = t_abs(v); *Pmax_out = (double)m; }
+    return k;
+}
 
 // =============================================================================================
 // C interface (ctypes)
@@ -797,6 +828,16 @@ int orc_dlqr(const double* A, const double* Bu, const double* Bl, const double* 
     if (iters_out) *iters_out = iters;
     if (P_out) std::copy(P.begin(), P.end(), P_out);
     return k;
+}
+
+int orc_dlqr_mp(int prec, const double* A, const double* Bu, const double* Bl, const double* G, const double* Q, const double* R, int n, int mu,
+                int ml, int N, double* Ku, int* iters_out, double* normdiff_trace, double* Pmax_out) {
+    if (prec == 0) return dlqr_mp<double>(A, Bu, Bl, G, Q, R, n, mu, ml, N, Ku, iters_out, normdiff_trace, Pmax_out);
+    if (prec == 1) return dlqr_mp<long double>(A, Bu, Bl, G, Q, R, n, mu, ml, N, Ku, iters_out, normdiff_trace, Pmax_out);
+#ifdef ORC_WITH_QUAD
+    if (prec == 2) return dlqr_mp<__float128>(A, Bu, Bl, G, Q, R, n, mu, ml, N, Ku, iters_out, normdiff_trace, Pmax_out);
+#endif
+    return -1;
 }
 
 // dlqr(mechanism, xd, vd, qd, wd, Ftaud, eqcids, Q, R, N) lqr_tracking.jl:73-122

@@ -224,6 +224,21 @@ def dlqr(A, Bu, Bl, G, Q, R, N):
     return dict(Ku=Ku, kexit=k, iters=iters.value, P=P)
 
 
+def dlqr_mp(A, Bu, Bl, G, Q, R, N, prec=2):
+    """dlqr (lqr.jl:141-184) with the recursion carried in prec 0 = Float64, 1 = long double (x87), 2 = binary128; Float64 inputs / outputs.
+    Also returns the trace of ||Pk - Pkp1||_F (the early-break quantity of lqr.jl:172) and max |P| at exit."""
+    A = _f64(A); n = A.shape[0]
+    Bu = _f64(Bu).reshape(n, -1); mu = Bu.shape[1]
+    Bl = _f64(Bl).reshape(n, -1); ml = Bl.shape[1]
+    G = _f64(G).reshape(ml, n)
+    Ku = np.zeros((N - 1, mu, n)); trace = np.zeros(N - 1); iters = C.c_int(0); pmax = C.c_double(0)
+    k = lib().orc_dlqr_mp(C.c_int(prec), _p(A), _p(Bu), _p(Bl), _p(G), _p(_f64(Q)), _p(_f64(R)), C.c_int(n), C.c_int(mu), C.c_int(ml), C.c_int(N),
+                          _p(Ku), C.byref(iters), _p(trace), C.byref(pmax))
+    if k < 0:
+        raise RuntimeError("orc_dlqr_mp: precision not built")
+    return dict(Ku=Ku, kexit=k, iters=iters.value, trace=trace[:iters.value], Pmax=pmax.value)
+
+
 def dlqr_batch(A, Bu, Bl, G, Q, R, N, nthreads=1):
     A = _f64(A); B, n = A.shape[0], A.shape[1]
     Bu = _f64(Bu).reshape(B, n, -1); mu = Bu.shape[2]

@@ -9,72 +9,90 @@ namespace orc {
 
 typedef std::vector<double> Mat;  // row-major, dimensions carried by the caller
 
+// The dense helpers are templated on the scalar so that the SAME restatement of dlqr can be run in Float64 (the reference's
+// arithmetic: every parity test uses this instantiation), in x87 extended precision (long double, eps 1.1e-19) and in IEEE
+// binary128 (__float128, eps 1.9e-34).  The wider instantiations exist for ONE purpose: to measure how much of a gain
+// difference between two Float64 implementations is rounding amplified by the recursion itself (tests/test_oracle_quad.py).
+inline double t_abs(double x) { return std::fabs(x); }
+inline long double t_abs(long double x) { return std::fabs(x); }
+inline double t_sqrt(double x) { return std::sqrt(x); }
+inline long double t_sqrt(long double x) { return std::sqrt(x); }
+#ifdef ORC_WITH_QUAD
+inline __float128 t_abs(__float128 x) { return x < 0 ? -x : x; }
+inline __float128 t_sqrt(__float128 x) {       // Newton on the double estimate: three steps reach binary128 accuracy
+    if (x <= 0) return 0;
+    __float128 y = (__float128)std::sqrt((double)x);
+    for (int i = 0; i < 3; i++) y = (y + x / y) / 2;
+    return y;
+}
+#endif
+
 // C[m x n] = A[m x k] * B[k x n]
-inline void mm(const double* A, const double* B, double* C, int m, int k, int n) {
+template <class T> inline void mm(const T* A, const T* B, T* C, int m, int k, int n) {
     for (int i = 0; i < m; i++) {
-        double* c = C + (size_t)i * n;
-        for (int j = 0; j < n; j++) c[j] = 0.0;
+        T* c = C + (size_t)i * n;
+        for (int j = 0; j < n; j++) c[j] = T(0.0);
         for (int p = 0; p < k; p++) {
-            double a = A[(size_t)i * k + p];
-            if (a == 0.0) continue;
-            const double* b = B + (size_t)p * n;
+            T a = A[(size_t)i * k + p];
+            if (a == T(0.0)) continue;
+            const T* b = B + (size_t)p * n;
             for (int j = 0; j < n; j++) c[j] += a * b[j];
         }
     }
 }
 // C[m x n] = A^T * B with A[k x m], B[k x n]
-inline void mtm(const double* A, const double* B, double* C, int m, int k, int n) {
-    for (int i = 0; i < m * n; i++) C[i] = 0.0;
+template <class T> inline void mtm(const T* A, const T* B, T* C, int m, int k, int n) {
+    for (int i = 0; i < m * n; i++) C[i] = T(0.0);
     for (int p = 0; p < k; p++)
         for (int i = 0; i < m; i++) {
-            double a = A[(size_t)p * m + i];
-            if (a == 0.0) continue;
-            const double* b = B + (size_t)p * n;
-            double* c = C + (size_t)i * n;
+            T a = A[(size_t)p * m + i];
+            if (a == T(0.0)) continue;
+            const T* b = B + (size_t)p * n;
+            T* c = C + (size_t)i * n;
             for (int j = 0; j < n; j++) c[j] += a * b[j];
         }
 }
 
 // In-place LU with partial pivoting (LAPACK getrf semantics); returns 0 on success, k+1 on exact zero pivot.
-inline int lu_factor(double* A, int n, int* piv) {
+template <class T> inline int lu_factor(T* A, int n, int* piv) {
     for (int k = 0; k < n; k++) {
         int p = k;
-        double best = std::fabs(A[(size_t)k * n + k]);
+        T best = t_abs(A[(size_t)k * n + k]);
         for (int i = k + 1; i < n; i++) {
-            double v = std::fabs(A[(size_t)i * n + k]);
+            T v = t_abs(A[(size_t)i * n + k]);
             if (v > best) { best = v; p = i; }
         }
         piv[k] = p;
-        if (best == 0.0) return k + 1;
+        if (best == T(0.0)) return k + 1;
         if (p != k)
             for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
-        double inv = 1.0 / A[(size_t)k * n + k];
+        T inv = T(1.0) / A[(size_t)k * n + k];
         for (int i = k + 1; i < n; i++) {
-            double l = A[(size_t)i * n + k] * inv;
+            T l = A[(size_t)i * n + k] * inv;
             A[(size_t)i * n + k] = l;
-            if (l == 0.0) continue;
+            if (l == T(0.0)) continue;
             for (int j = k + 1; j < n; j++) A[(size_t)i * n + j] -= l * A[(size_t)k * n + j];
         }
     }
     return 0;
 }
 // Solve A X = B for X (B is n x nrhs, overwritten)
-inline void lu_solve(const double* LU, const int* piv, int n, double* B, int nrhs) {
+template <class T> inline void lu_solve(const T* LU, const int* piv, int n, T* B, int nrhs) {
     for (int k = 0; k < n; k++)
         if (piv[k] != k)
             for (int j = 0; j < nrhs; j++) std::swap(B[(size_t)k * nrhs + j], B[(size_t)piv[k] * nrhs + j]);
     for (int k = 0; k < n; k++)
         for (int i = k + 1; i < n; i++) {
-            double l = LU[(size_t)i * n + k];
-            if (l == 0.0) continue;
+            T l = LU[(size_t)i * n + k];
+            if (l == T(0.0)) continue;
             for (int j = 0; j < nrhs; j++) B[(size_t)i * nrhs + j] -= l * B[(size_t)k * nrhs + j];
         }
     for (int k = n - 1; k >= 0; k--) {
-        double inv = 1.0 / LU[(size_t)k * n + k];
+        T inv = T(1.0) / LU[(size_t)k * n + k];
         for (int j = 0; j < nrhs; j++) B[(size_t)k * nrhs + j] *= inv;
         for (int i = 0; i < k; i++) {
-            double u = LU[(size_t)i * n + k];
-            if (u == 0.0) continue;
+            T u = LU[(size_t)i * n + k];
+            if (u == T(0.0)) continue;
             for (int j = 0; j < nrhs; j++) B[(size_t)i * nrhs + j] -= u * B[(size_t)k * nrhs + j];
         }
     }

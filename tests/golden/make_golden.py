@@ -8,6 +8,8 @@ line = open("/root/reference/examples/trackingLQR_triple_cartpole.jl").readline(
 vals = [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line.split("=", 1)[1])]
 assert len(vals) == 1000
 np.save(__file__.replace("make_golden.py", "triple_cartpole_U.npy"), np.array(vals))
+# the same numbers one per line for tools/dump_golden.jl (the Julia side reads no .npy)
+open(__file__.replace("make_golden.py", "triple_cartpole_U.txt"), "w").write("\n".join(repr(float(v)) for v in vals) + "\n")
 
 # parsed parameters of the Sawyer arm (reference examples/examples_files/sawyer_arm.urdf): masses, COMs, inertia tensors,
 # joint origins/axes -- numbers only, so that the GPU box (which has no /root/reference) can build the mechanism.

@@ -38,6 +38,17 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
 
 
+def gain_err(a, b, floor=1e-3):
+    """ELEMENT-relative error of a gain table against its reference: max_ij |a_ij - b_ij| / max(|b_ij|, floor * s_row),
+    s_row = the largest |b| of the entry's own gain row (last axis).  A global scale lets the small entries of a row whose large entries are ~350
+    be wrong by 3.5e-7 absolute; here an entry may only be off by 1e-9 of ITS OWN magnitude, down to entries 1000x smaller than the row's largest
+    (below that an entry is rounding residue of the row's large entries -- structurally zero columns come out as 1e-13 in every implementation)."""
+    a = np.asarray(a, dtype=float); b = np.asarray(b, dtype=float)
+    scale = np.maximum(np.abs(b), floor * np.abs(b).max(axis=-1, keepdims=True))
+    scale = np.where(scale == 0.0, 1.0, scale)
+    return float((np.abs(a - b) / scale).max())
+
+
 def cartpole_states(cc, mech, B, seed=1, ymax=0.5, phimax=0.2):
     """y0 ~ U(-0.5,0.5), theta0 ~ U(-0.2,0.2), zero velocity"""
     rng = np.random.default_rng(seed)
