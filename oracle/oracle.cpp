@@ -317,6 +317,14 @@ inline void eval_f(const Mech& M, Work& W) { residual<double>(M, W.z.data(), W.s
 
 // newton! + lineSearch!: eps = 1e-10, newtonIter = 100, lineIter = 10 by default.
 // Returns the number of Newton iterations used, negative if not converged / singular.
+// Instrumentation for tests/test_gpu_fullsize.py (never changes the iterates): with a band tau > 1 set, a Newton iteration counts as MARGINAL
+// when its termination decision `nd < eps && normf1 < eps` would come out differently with nd and normf1 scaled by 1/tau or by tau.  After the
+// first (nearly exact) Newton step of a mildly nonlinear time step the next step is rounding noise amplified by the KKT inverse, ~1e-11..1e-9 --
+// right at the default eps = 1e-10 -- so its termination decision, and with it the ITERATION COUNT, is decided by rounding and differs between
+// any two Float64 implementations (already between this file's dense and block-sparse solvers: tests/test_oracle_control.py).
+static double g_marginal_band = 0.0;
+static thread_local long g_marginal_count = 0;
+
 int newton(const Mech& M, Work& W, double eps, int newton_iter, int line_iter, int solver) {
     const int ns = 6 * M.nb, ml = M.ml;
     eval_f(M, W);
@@ -341,6 +349,10 @@ int newton(const Mech& M, Work& W, double eps, int newton_iter, int line_iter, i
         for (int i = 0; i < ns; i++) { double d = W.s[i] - W.s0[i]; nd += d * d; }
         for (int i = 0; i < ml; i++) { double d = W.lam[i] - W.lam0[i]; nd += d * d; }
         nd = std::sqrt(nd);
+        if (g_marginal_band > 1.0) {
+            const double t = g_marginal_band;
+            if ((nd / t < eps && normf1 / t < eps) != (nd * t < eps && normf1 * t < eps)) g_marginal_count++;
+        }
         if (nd < eps && normf1 < eps) return n;
         normf0 = normf1;
     }
@@ -685,6 +697,34 @@ int dlqr_mp(const double* A_, const double* Bu_, const double* Bl_, const double
     return k;
 }
 
+// tracking dlqr (lqr_tracking.jl:73-122) with the recursion in a wider scalar; every linearisation is the Float64 one (the data of the problem)
+template <class T>
+int tracking_dlqr_mp(Mech& M, const double* traj, const double* Ftau, const int* eqc_idx, int nu, const double* Q_, const double* R_, int N,
+                     double eps, int newton_iter, int line_iter, double* Ku, int* iters_out) {
+    const int n = 12 * M.nb, ml = M.ml;
+    Work W(M);
+    Mat A((size_t)n * n), Bu((size_t)n * nu), Bl((size_t)n * ml), G((size_t)ml * n);
+    auto up = [](const double* p, size_t cnt) { std::vector<T> v(cnt); for (size_t i = 0; i < cnt; i++) v[i] = (T)p[i]; return v; };
+    std::vector<T> Q = up(Q_, (size_t)n * n), R = up(R_, (size_t)nu * nu), P = Q, Kk((size_t)nu * n);
+    std::vector<double> lam(ml, 0.0);
+    RicWorkT<T> w;
+    int k = 0, iters = 0;
+    T nd;
+    for (k = N - 1; k >= 1; k--) {
+        iters++;
+        linearize(M, W, traj + (size_t)(k - 1) * 13 * M.nb, Ftau + (size_t)(k - 1) * nu, eqc_idx, nu, lam.data(), eps, newton_iter, line_iter,
+                  A.data(), Bu.data(), Bl.data(), G.data());   // lqr_tracking.jl:88
+        std::vector<T> At = up(A.data(), A.size()), But = up(Bu.data(), Bu.size()), Blt = up(Bl.data(), Bl.size()), Gt = up(G.data(), G.size());
+        bool brk = riccati_step<T>(At.data(), But.data(), Blt.data(), Gt.data(), Q.data(), R.data(), n, nu, ml, P, Kk.data(), w, &nd);
+        for (int i = 0; i < nu * n; i++) Ku[(size_t)(k - 1) * nu * n + i] = (double)Kk[i];
+        if (brk) break;
+    }
+    if (k < 1) k = 1;
+    for (int k2 = k - 1; k2 >= 1; k2--) std::memcpy(Ku + (size_t)(k2 - 1) * nu * n, Ku + (size_t)k2 * nu * n, sizeof(double) * nu * n);
+    if (iters_out) *iters_out = iters;
+    return k;
+}
+
 // =============================================================================================
 // C interface (ctypes)
 // =============================================================================================
@@ -760,6 +800,11 @@ int orc_solve_both(void* h, const double* z, const double* s, const double* lam,
     return (a ? 0 : 1) + (b ? 0 : 2);
 }
 
+static int* g_marginal_out = nullptr;
+// marginal_out [B] receives, per system, the number of Newton iterations of the NEXT orc_simulate call whose termination decision is
+// marginal within the band (see newton); band <= 1 or NULL switches the instrumentation off again
+void orc_set_marginal(double band, int* marginal_out) { g_marginal_band = band; g_marginal_out = marginal_out; }
+
 // simulate!: states [B][nb][13] (xc,qc,vc,wc) in/out, lambdas [B][ml] in/out,
 // storage [steps][B][nb][13] or NULL, iters_out [B] = total Newton iterations (negated if any step failed)
 void orc_simulate(void* h, int B, double* states, double* lambdas, int k0, int steps, const orc_ctrl* C, double eps, int newton_iter,
@@ -774,12 +819,14 @@ void orc_simulate(void* h, int B, double* states, double* lambdas, int k0, int s
             double* st = states + (size_t)sys * sn;
             double* lam = lambdas + (size_t)sys * M.ml;
             int tot = 0; bool bad = false;
+            g_marginal_count = 0;
             for (int k = 0; k < steps; k++) {
                 if (storage) std::memcpy(storage + ((size_t)k * B + sys) * sn, st, sizeof(double) * sn);
                 int it = sim_step(M, W, C, sys, k0 + k, st, lam, eps, newton_iter, line_iter, solver);
                 if (it < 0) { bad = true; tot += -it > 1000 ? 0 : -it; } else tot += it;
             }
             if (iters_out) iters_out[sys] = bad ? -tot : tot;
+            if (g_marginal_out) g_marginal_out[sys] = (int)g_marginal_count;
         }
     };
     if (nthreads == 1) { run(0, B); return; }
@@ -863,6 +910,17 @@ int orc_tracking_dlqr(void* h, const double* traj, const double* Ftau, const int
     for (int k2 = k - 1; k2 >= 1; k2--) std::memcpy(Ku + (size_t)(k2 - 1) * nu * n, Ku + (size_t)k2 * nu * n, sizeof(double) * nu * n);
     if (iters_out) *iters_out = iters;
     return k;
+}
+
+int orc_tracking_dlqr_mp(int prec, void* h, const double* traj, const double* Ftau, const int* eqc_idx, int nu, const double* Q, const double* R,
+                         int N, double eps, int newton_iter, int line_iter, double* Ku, int* iters_out) {
+    Mech& M = *(Mech*)h;
+    if (prec == 0) return tracking_dlqr_mp<double>(M, traj, Ftau, eqc_idx, nu, Q, R, N, eps, newton_iter, line_iter, Ku, iters_out);
+    if (prec == 1) return tracking_dlqr_mp<long double>(M, traj, Ftau, eqc_idx, nu, Q, R, N, eps, newton_iter, line_iter, Ku, iters_out);
+#ifdef ORC_WITH_QUAD
+    if (prec == 2) return tracking_dlqr_mp<__float128>(M, traj, Ftau, eqc_idx, nu, Q, R, N, eps, newton_iter, line_iter, Ku, iters_out);
+#endif
+    return -1;
 }
 
 // batched LQR synthesis for the CPU baseline: B independent (A,Bu,Bl,G,Q,R) problems over threads

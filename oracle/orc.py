@@ -177,15 +177,20 @@ class OracleMech:
 
     # ---- simulate!
     def simulate(self, states, steps, ctrl=None, lambdas=None, k0=1, eps=1e-10, newton_iter=100, line_iter=10, solver=1, record=False,
-                 nthreads=1):
+                 nthreads=1, marginal_band=0.0):
         states = np.array(states, dtype=np.float64, copy=True).reshape(-1, self.nb, 13)
         B = states.shape[0]
         lambdas = np.zeros((B, self.ml)) if lambdas is None else np.array(lambdas, dtype=np.float64, copy=True).reshape(B, self.ml)
         storage = np.zeros((steps, B, self.nb, 13)) if record else None
         iters = np.zeros(B, dtype=np.int32)
+        marginal = np.zeros(B, dtype=np.int32)
+        if marginal_band > 1.0:      # count the Newton iterations whose termination decision is rounding-marginal (oracle.cpp: newton)
+            lib().orc_set_marginal(C.c_double(marginal_band), _p(marginal))
         lib().orc_simulate(self.h, C.c_int(B), _p(states), _p(lambdas), C.c_int(k0), C.c_int(steps), C.byref(ctrl) if ctrl is not None else None,
                            C.c_double(eps), C.c_int(newton_iter), C.c_int(line_iter), C.c_int(solver), _p(storage), _p(iters), C.c_int(nthreads))
-        return dict(states=states, lambdas=lambdas, storage=storage, iters=iters)
+        if marginal_band > 1.0:
+            lib().orc_set_marginal(C.c_double(0.0), None)
+        return dict(states=states, lambdas=lambdas, storage=storage, iters=iters, marginal=marginal)
 
     def control(self, ctrl, sys, k, state):
         u = np.zeros(self.ne)
@@ -202,11 +207,16 @@ class OracleMech:
                                  C.c_int(line_iter), _p(A), _p(Bu), _p(Bl), _p(G))
         return dict(A=A, Bu=Bu, Bl=Bl, G=G, lam=lam, iters=it)
 
-    def tracking_dlqr(self, traj, Ftau, eqc_idx, Q, R, eps=1e-10, newton_iter=100, line_iter=10):
+    def tracking_dlqr(self, traj, Ftau, eqc_idx, Q, R, eps=1e-10, newton_iter=100, line_iter=10, prec=None):
+        """prec None: the literal Float64 loop; 0/1/2: orc_tracking_dlqr_mp (Float64 linearisations, recursion in Float64 / x87 / binary128)"""
         traj = _f64(traj).reshape(-1, self.nb, 13)
         N = traj.shape[0]
         eqc_idx = _i32(eqc_idx); nu = eqc_idx.size
         Ku = np.zeros((N - 1, nu, self.n)); iters = C.c_int(0)
+        if prec is not None:
+            k = lib().orc_tracking_dlqr_mp(C.c_int(prec), self.h, _p(traj), _p(_f64(Ftau)), _p(eqc_idx), C.c_int(nu), _p(_f64(Q)), _p(_f64(R)), C.c_int(N),
+                                           C.c_double(eps), C.c_int(newton_iter), C.c_int(line_iter), _p(Ku), C.byref(iters))
+            return dict(Ku=Ku, kexit=k, iters=iters.value)
         k = lib().orc_tracking_dlqr(self.h, _p(traj), _p(_f64(Ftau)), _p(eqc_idx), C.c_int(nu), _p(_f64(Q)), _p(_f64(R)), C.c_int(N),
                                     C.c_double(eps), C.c_int(newton_iter), C.c_int(line_iter), _p(Ku), C.byref(iters))
         return dict(Ku=Ku, kexit=k, iters=iters.value)
