@@ -132,18 +132,18 @@ Mech* build_mech(int nb, int ne, int nj, double dt, double g, const double* mass
 // ---------------------------------------------------------------------------------------------
 // Newton workspace + KKT assembly (analytic blocks)
 // ---------------------------------------------------------------------------------------------
-struct Work {
+template <class T> struct WorkT {
     int n;                         // 6 nb + ml
-    std::vector<double> z, s, lam, s0, lam0, f, delta, u;
-    std::vector<double> Md;        // dense KKT
+    std::vector<T> z, s, lam, s0, lam0, f, delta, u;
+    std::vector<T> Md;             // dense KKT
     std::vector<int> piv;
-    std::vector<double> pool, dinv, tmp;   // sparse blocks, diagonal inverses
+    std::vector<T> pool, dinv, tmp;        // sparse blocks, diagonal inverses
     std::vector<int> dinv_off;
     std::vector<std::vector<int>> later;   // per dfs position: later neighbours (node index)
-    explicit Work(const Mech& M) {
+    explicit WorkT(const Mech& M) {
         n = 6 * M.nb + M.ml;
-        z.resize(13 * M.nb); s.resize(6 * M.nb); lam.assign(M.ml, 0.0); s0 = s; lam0 = lam;
-        f.resize(n); delta.resize(n); u.assign(M.ne, 0.0);
+        z.resize(13 * M.nb); s.resize(6 * M.nb); lam.assign(M.ml, T(0.0)); s0 = s; lam0 = lam;
+        f.resize(n); delta.resize(n); u.assign(M.ne, T(0.0));
         Md.resize((size_t)n * n); piv.resize(n);
         pool.resize(M.pool); tmp.resize(16 * 16);
         const int N = M.nnodes;
@@ -161,31 +161,34 @@ struct Work {
     }
 };
 
-inline double norm2(const double* a, int n) { double s = 0; for (int i = 0; i < n; i++) s += a[i] * a[i]; return std::sqrt(s); }
+typedef WorkT<double> Work;       // the reference's arithmetic; WorkT<Count> (oracle/flopcount: orc_count_flops) only COUNTS operations
+
+template <class T> inline T norm2(const T* a, int n) { T s = T(0.0); for (int i = 0; i < n; i++) s += a[i] * a[i]; return orc::sqrt(s); }
 
 // per-joint analytic blocks: G at (x2,q2) and Gv = d g(x3,q3)/d(v2,w2) for parent / child
-void joint_blocks(const Mech& M, const Joint& J, const double* z, const double* s, double* Ga, double* Gb, double* Gva, double* Gvb) {
-    Pose<double> a2 = J.parent >= 0 ? body_pose2(z, J.parent) : origin_pose<double>();
-    Pose<double> b2 = body_pose2(z, J.child);
+template <class T>
+void joint_blocks(const Mech& M, const Joint& J, const T* z, const T* s, T* Ga, T* Gb, T* Gva, T* Gvb) {
+    Pose<T> a2 = J.parent >= 0 ? body_pose2(z, J.parent) : origin_pose<T>();
+    Pose<T> b2 = body_pose2(z, J.child);
     joint_G(J, a2, b2, Ga, Gb);
-    Pose<double> a3 = origin_pose<double>(), b3;
-    double Ta[9], Tb[9];
+    Pose<T> a3 = origin_pose<T>(), b3;
+    T Ta[9], Tb[9];
     if (J.parent >= 0) {
-        const double* sa = s + 6 * J.parent;
-        next_pose<double>(a2, {sa[0], sa[1], sa[2]}, {sa[3], sa[4], sa[5]}, M.dt, a3);
+        const T* sa = s + 6 * J.parent;
+        next_pose<T>(a2, {sa[0], sa[1], sa[2]}, {sa[3], sa[4], sa[5]}, M.dt, a3);
         T_omega(sa + 3, M.dt, Ta);
     }
-    const double* sb = s + 6 * J.child;
-    next_pose<double>(b2, {sb[0], sb[1], sb[2]}, {sb[3], sb[4], sb[5]}, M.dt, b3);
+    const T* sb = s + 6 * J.child;
+    next_pose<T>(b2, {sb[0], sb[1], sb[2]}, {sb[3], sb[4], sb[5]}, M.dt, b3);
     T_omega(sb + 3, M.dt, Tb);
-    double G3a[36], G3b[36];
+    T G3a[36], G3b[36];
     joint_G(J, a3, b3, G3a, G3b);
     for (int r = 0; r < J.dim; r++) {
         for (int c = 0; c < 3; c++) {
-            Gvb[r * 6 + c] = G3b[r * 6 + c] * M.dt;
+            Gvb[r * 6 + c] = G3b[r * 6 + c] * T(M.dt);
             Gvb[r * 6 + 3 + c] = G3b[r * 6 + 3] * Tb[0 * 3 + c] + G3b[r * 6 + 4] * Tb[1 * 3 + c] + G3b[r * 6 + 5] * Tb[2 * 3 + c];
             if (J.parent >= 0) {
-                Gva[r * 6 + c] = G3a[r * 6 + c] * M.dt;
+                Gva[r * 6 + c] = G3a[r * 6 + c] * T(M.dt);
                 Gva[r * 6 + 3 + c] = G3a[r * 6 + 3] * Ta[0 * 3 + c] + G3a[r * 6 + 4] * Ta[1 * 3 + c] + G3a[r * 6 + 5] * Ta[2 * 3 + c];
             }
         }
@@ -218,16 +221,17 @@ void assemble_dense(const Mech& M, Work& W) {
 }
 
 // mixed-node block LDU in dfs_list order: ldu_factorization! / ldu_backsubstitution!
-bool solve_sparse(const Mech& M, Work& W) {
+template <class T>
+bool solve_sparse(const Mech& M, WorkT<T>& W) {
     const int N = M.nnodes, nb = M.nb, ne = M.ne;
-    std::fill(W.pool.begin(), W.pool.end(), 0.0);
-    auto B = [&](int i, int j) -> double* { return W.pool.data() + M.blk[(size_t)i * N + j]; };
-    double D[36], Ga[36], Gb[36], Gva[36], Gvb[36];
+    std::fill(W.pool.begin(), W.pool.end(), T(0.0));
+    auto B = [&](int i, int j) -> T* { return W.pool.data() + M.blk[(size_t)i * N + j]; };
+    T D[36], Ga[36], Gb[36], Gva[36], Gvb[36];
     for (int b = 0; b < nb; b++) {
         body_D(M.m[b], &M.J[9 * b], M.dt, &W.s[6 * b + 3], D);
-        std::memcpy(B(ne + b, ne + b), D, sizeof(D));
+        std::copy(D, D + 36, B(ne + b, ne + b));
     }
-    for (int e = 0; e < ne; e++) { double* d = B(e, e); int c = M.eqc_dim[e]; for (int i = 0; i < c; i++) d[i * c + i] = M.reg; }
+    for (int e = 0; e < ne; e++) { T* d = B(e, e); int c = M.eqc_dim[e]; for (int i = 0; i < c; i++) d[i * c + i] = T(M.reg); }
     for (const Joint& J : M.joints) {
         joint_blocks(M, J, W.z.data(), W.s.data(), Ga, Gb, Gva, Gvb);
         const int e = J.eqc, c = M.eqc_dim[e], r0 = J.row0 - M.eqc_row0[e];
@@ -242,63 +246,63 @@ bool solve_sparse(const Mech& M, Work& W) {
             }
     }
     // rhs
-    std::vector<double>& x = W.delta;
+    std::vector<T>& x = W.delta;
     x = W.f;
     // factorisation
     for (int i = 0; i < N; i++) {
         const int c = M.dfs_list[i] - 1, dc = M.node_dim[c];
-        double* Dinv = W.dinv.data() + W.dinv_off[c];
+        T* Dinv = W.dinv.data() + W.dinv_off[c];
         if (!small_inv(B(c, c), Dinv, dc)) return false;
         const std::vector<int>& lat = W.later[i];
         for (int p : lat) {
             const int dp = M.node_dim[p];
-            double* Mpc = B(p, c);
-            double* L = W.tmp.data();
+            T* Mpc = B(p, c);
+            T* L = W.tmp.data();
             mm(Mpc, Dinv, L, dp, dc, dc);                        // L_pc = M_pc D_c^-1
             for (int q : lat) {
                 const int dq = M.node_dim[q];
-                const double* Mcq = B(c, q);
-                double* Mpq = B(p, q);
+                const T* Mcq = B(c, q);
+                T* Mpq = B(p, q);
                 for (int a = 0; a < dp; a++)
                     for (int k = 0; k < dc; k++) {
-                        double l = L[a * dc + k];
-                        if (l == 0.0) continue;
+                        T l = L[a * dc + k];
+                        if (l == T(0.0)) continue;
                         for (int b2 = 0; b2 < dq; b2++) Mpq[a * dq + b2] -= l * Mcq[k * dq + b2];
                     }
             }
-            std::memcpy(Mpc, L, sizeof(double) * dp * dc);
+            std::copy(L, L + dp * dc, Mpc);
         }
         for (int q : lat) {                                      // U_cq = D_c^-1 M_cq
             const int dq = M.node_dim[q];
-            double* Mcq = B(c, q);
-            double* U = W.tmp.data();
+            T* Mcq = B(c, q);
+            T* U = W.tmp.data();
             mm(Dinv, Mcq, U, dc, dc, dq);
-            std::memcpy(Mcq, U, sizeof(double) * dc * dq);
+            std::copy(U, U + dc * dq, Mcq);
         }
     }
     // forward substitution
     for (int i = 0; i < N; i++) {
         const int c = M.dfs_list[i] - 1, dc = M.node_dim[c];
-        const double* xc = x.data() + M.node_off[c];
+        const T* xc = x.data() + M.node_off[c];
         for (int p : W.later[i]) {
             const int dp = M.node_dim[p];
-            const double* L = B(p, c);
-            double* xp = x.data() + M.node_off[p];
-            for (int a = 0; a < dp; a++) { double s = 0; for (int k = 0; k < dc; k++) s += L[a * dc + k] * xc[k]; xp[a] -= s; }
+            const T* L = B(p, c);
+            T* xp = x.data() + M.node_off[p];
+            for (int a = 0; a < dp; a++) { T s = T(0.0); for (int k = 0; k < dc; k++) s += L[a * dc + k] * xc[k]; xp[a] -= s; }
         }
     }
     // diagonal + backward substitution
     for (int i = N - 1; i >= 0; i--) {
         const int c = M.dfs_list[i] - 1, dc = M.node_dim[c];
-        double* xc = x.data() + M.node_off[c];
-        const double* Dinv = W.dinv.data() + W.dinv_off[c];
-        double t[16];
-        for (int a = 0; a < dc; a++) { double s = 0; for (int k = 0; k < dc; k++) s += Dinv[a * dc + k] * xc[k]; t[a] = s; }
+        T* xc = x.data() + M.node_off[c];
+        const T* Dinv = W.dinv.data() + W.dinv_off[c];
+        T t[16];
+        for (int a = 0; a < dc; a++) { T s = T(0.0); for (int k = 0; k < dc; k++) s += Dinv[a * dc + k] * xc[k]; t[a] = s; }
         for (int q : W.later[i]) {
             const int dq = M.node_dim[q];
-            const double* U = B(c, q);
-            const double* xq = x.data() + M.node_off[q];
-            for (int a = 0; a < dc; a++) { double s = 0; for (int k = 0; k < dq; k++) s += U[a * dq + k] * xq[k]; t[a] -= s; }
+            const T* U = B(c, q);
+            const T* xq = x.data() + M.node_off[q];
+            for (int a = 0; a < dc; a++) { T s = T(0.0); for (int k = 0; k < dq; k++) s += U[a * dq + k] * xq[k]; t[a] -= s; }
         }
         for (int a = 0; a < dc; a++) xc[a] = t[a];
     }
@@ -313,7 +317,9 @@ bool solve_dense(const Mech& M, Work& W) {
     return true;
 }
 
-inline void eval_f(const Mech& M, Work& W) { residual<double>(M, W.z.data(), W.s.data(), W.lam.data(), W.u.data(), W.f.data()); }
+template <class T> inline void eval_f(const Mech& M, WorkT<T>& W) { residual<T>(M, W.z.data(), W.s.data(), W.lam.data(), W.u.data(), W.f.data()); }
+inline bool solve_any(const Mech& M, WorkT<double>& W, int solver);
+template <class T> inline bool solve_any(const Mech& M, WorkT<T>& W, int) { return solve_sparse<T>(M, W); }
 
 // newton! + lineSearch!: eps = 1e-10, newtonIter = 100, lineIter = 10 by default.
 // Returns the number of Newton iterations used, negative if not converged / singular.
@@ -325,39 +331,42 @@ inline void eval_f(const Mech& M, Work& W) { residual<double>(M, W.z.data(), W.s
 static double g_marginal_band = 0.0;
 static thread_local long g_marginal_count = 0;
 
-int newton(const Mech& M, Work& W, double eps, int newton_iter, int line_iter, int solver) {
+template <class T>
+int newton(const Mech& M, WorkT<T>& W, double eps, int newton_iter, int line_iter, int solver) {
     const int ns = 6 * M.nb, ml = M.ml;
     eval_f(M, W);
-    double normf0 = norm2(W.f.data(), W.n);
+    T normf0 = norm2(W.f.data(), W.n);
     for (int n = 1; n <= newton_iter; n++) {
         eval_f(M, W);   // setentries!: residual at the current iterate
-        bool ok = solver == 0 ? solve_dense(M, W) : solve_sparse(M, W);
+        bool ok = solve_any(M, W, solver);
         if (!ok) return -1000 - n;
         W.s0 = W.s; W.lam0 = W.lam;
-        double normf1 = normf0;
+        T normf1 = normf0;
         int scale = 0;
         for (int it = 0; it < line_iter + 1; it++) {
-            double a = 1.0 / (double)(1 << scale);
+            T a = T(1.0 / (double)(1 << scale));
             for (int i = 0; i < ns; i++) W.s[i] = W.s0[i] - a * W.delta[i];
             for (int i = 0; i < ml; i++) W.lam[i] = W.lam0[i] - a * W.delta[ns + i];
             eval_f(M, W);
             normf1 = norm2(W.f.data(), W.n);
-            if (normf1 >= normf0) scale++;
+            if (val(normf1) >= val(normf0)) scale++;
             else break;
         }
-        double nd = 0;
-        for (int i = 0; i < ns; i++) { double d = W.s[i] - W.s0[i]; nd += d * d; }
-        for (int i = 0; i < ml; i++) { double d = W.lam[i] - W.lam0[i]; nd += d * d; }
-        nd = std::sqrt(nd);
+        T nd = T(0.0);
+        for (int i = 0; i < ns; i++) { T d = W.s[i] - W.s0[i]; nd += d * d; }
+        for (int i = 0; i < ml; i++) { T d = W.lam[i] - W.lam0[i]; nd += d * d; }
+        nd = orc::sqrt(nd);
         if (g_marginal_band > 1.0) {
-            const double t = g_marginal_band;
-            if ((nd / t < eps && normf1 / t < eps) != (nd * t < eps && normf1 * t < eps)) g_marginal_count++;
+            const double t = g_marginal_band, ndv = val(nd), nfv = val(normf1);
+            if ((ndv / t < eps && nfv / t < eps) != (ndv * t < eps && nfv * t < eps)) g_marginal_count++;
         }
-        if (nd < eps && normf1 < eps) return n;
+        if (val(nd) < eps && val(normf1) < eps) return n;
         normf0 = normf1;
     }
     return -newton_iter;
 }
+
+inline bool solve_any(const Mech& M, WorkT<double>& W, int solver) { return solver == 0 ? solve_dense(M, W) : solve_sparse<double>(M, W); }
 
 // ---------------------------------------------------------------------------------------------
 // controllers
@@ -921,6 +930,62 @@ int orc_tracking_dlqr_mp(int prec, void* h, const double* traj, const double* Ft
     if (prec == 2) return tracking_dlqr_mp<__float128>(M, traj, Ftau, eqc_idx, nu, Q, R, N, eps, newton_iter, line_iter, Ku, iters_out);
 #endif
     return -1;
+}
+
+// EXACT floating-point operation count of ONE newton! solve of the literal algorithm ("exact count from the oracle instrumented
+// with a counting scalar type"): the templated Newton solve (residual, analytic KKT blocks, mixed-node block LDU in dfs_list order,
+// back-substitution, line search) instantiated with orc::Count at the knot `state` [nb][13] with warm start `lam` [ml] and inputs u [ne].
+// out[0..4] = adds, muls, divs, sqrts, compares over the whole solve; out[5] = Newton iterations it took.  Dividing by the iterations gives
+// flops per Newton iteration (each iteration = 1 factorisation + solve + >= 1 residual evaluation of the line search; the one initial residual
+// evaluation is included in the total).
+int orc_count_flops(void* h, const double* state, const double* lam, const double* u, double eps, int newton_iter, int line_iter, long long* out) {
+    Mech& M = *(Mech*)h;
+    WorkT<Count> W(M);
+    std::vector<double> z(13 * M.nb);
+    knot_from_state(M, state, z.data());
+    for (int i = 0; i < 13 * M.nb; i++) W.z[i] = Count(z[i]);
+    for (int b = 0; b < M.nb; b++) for (int i = 0; i < 6; i++) W.s[6 * b + i] = Count(state[13 * b + 7 + i]);
+    for (int i = 0; i < M.ml; i++) W.lam[i] = Count(lam ? lam[i] : 0.0);
+    for (int e = 0; e < M.ne; e++) W.u[e] = Count(u ? u[e] : 0.0);
+    flop_tally() = FlopTally();
+    int it = newton<Count>(M, W, eps, newton_iter, line_iter, 1);
+    const FlopTally& t = flop_tally();
+    out[0] = t.add; out[1] = t.mul; out[2] = t.div; out[3] = t.sqrt_; out[4] = t.cmp; out[5] = it;
+    return it;
+}
+
+// The same count over a closed-loop ROLLOUT of one system: simulate! with the control law evaluated in Float64 (its 2 nu n flops are not
+// counted) and every newton! solve run in the counting scalar, which performs the identical operations in the identical order, so the
+// trajectory is bit-identical to orc_simulate's.  state [nb][13] and lam [ml] are updated in place; out[0..4] = adds, muls, divs, sqrts,
+// compares summed over the steps, out[5] = total Newton iterations.  flops per sim step = (out[0] + .. + out[3]) / steps.
+int orc_count_flops_rollout(void* h, double* state, double* lam, const orc_ctrl* C, int sys, int k0, int steps, double eps, int newton_iter,
+                            int line_iter, long long* out) {
+    Mech& M = *(Mech*)h;
+    Work Wd(M);
+    WorkT<Count> W(M);
+    FlopTally sum;
+    long long iters = 0;
+    for (int k = 0; k < steps; k++) {
+        knot_from_state(M, state, Wd.z.data());
+        control(M, Wd, C, sys, k0 + k, state);
+        for (int i = 0; i < 13 * M.nb; i++) W.z[i] = Count(Wd.z[i]);
+        for (int b = 0; b < M.nb; b++) for (int i = 0; i < 6; i++) W.s[6 * b + i] = Count(state[13 * b + 7 + i]);
+        for (int i = 0; i < M.ml; i++) W.lam[i] = Count(lam[i]);
+        for (int e = 0; e < M.ne; e++) W.u[e] = Count(Wd.u[e]);
+        flop_tally() = FlopTally();
+        int it = newton<Count>(M, W, eps, newton_iter, line_iter, 1);
+        const FlopTally& t = flop_tally();
+        sum.add += t.add; sum.mul += t.mul; sum.div += t.div; sum.sqrt_ += t.sqrt_; sum.cmp += t.cmp;
+        if (it < 0) return it;
+        iters += it;
+        for (int b = 0; b < M.nb; b++) {
+            for (int i = 0; i < 7; i++) state[13 * b + i] = Wd.z[13 * b + i];
+            for (int i = 0; i < 6; i++) state[13 * b + 7 + i] = W.s[6 * b + i].v;
+        }
+        for (int i = 0; i < M.ml; i++) lam[i] = W.lam[i].v;
+    }
+    out[0] = sum.add; out[1] = sum.mul; out[2] = sum.div; out[3] = sum.sqrt_; out[4] = sum.cmp; out[5] = iters;
+    return 0;
 }
 
 // batched LQR synthesis for the CPU baseline: B independent (A,Bu,Bl,G,Q,R) problems over threads

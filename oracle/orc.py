@@ -192,6 +192,31 @@ class OracleMech:
             lib().orc_set_marginal(C.c_double(0.0), None)
         return dict(states=states, lambdas=lambdas, storage=storage, iters=iters, marginal=marginal)
 
+    def count_flops(self, state, lam=None, u=None, eps=1e-10, newton_iter=100, line_iter=10):
+        """exact floating-point operation count of ONE literal newton! solve at `state` [nb][13] (oracle.cpp: orc_count_flops)"""
+        out = np.zeros(6, dtype=np.int64)
+        lam = np.zeros(self.ml) if lam is None else _f64(lam)
+        u = np.zeros(self.ne) if u is None else _f64(u)
+        lib().orc_count_flops(self.h, _p(_f64(state)), _p(lam), _p(u), C.c_double(eps), C.c_int(newton_iter), C.c_int(line_iter), _p(out))
+        add, mul, div, sq, cmp_, it = (int(v) for v in out)
+        return dict(add=add, mul=mul, div=div, sqrt=sq, compare=cmp_, iterations=it, flops=add + mul + div + sq,
+                    flops_per_iteration=(add + mul + div + sq) / max(it, 1))
+
+    def count_flops_rollout(self, state, steps, ctrl=None, sys=0, lam=None, k0=1, eps=1e-10, newton_iter=100, line_iter=10):
+        """exact operation count of the literal algorithm over a closed-loop rollout of ONE system (oracle.cpp: orc_count_flops_rollout);
+        returns the counts, the final state (bit-identical to simulate()) and flops per sim step / per Newton iteration"""
+        st = np.array(state, dtype=np.float64, copy=True).reshape(self.nb, 13)
+        lam = np.zeros(self.ml) if lam is None else np.array(lam, dtype=np.float64, copy=True)
+        out = np.zeros(6, dtype=np.int64)
+        rc = lib().orc_count_flops_rollout(self.h, _p(st), _p(lam), C.byref(ctrl) if ctrl is not None else None, C.c_int(sys), C.c_int(k0), C.c_int(steps),
+                                           C.c_double(eps), C.c_int(newton_iter), C.c_int(line_iter), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"orc_count_flops_rollout: Newton failure {rc}")
+        add, mul, div, sq, cmp_, it = (int(v) for v in out)
+        fl = add + mul + div + sq
+        return dict(add=add, mul=mul, div=div, sqrt=sq, compare=cmp_, iterations=it, flops=fl, state=st, lam=lam,
+                    flops_per_step=fl / steps, flops_per_iteration=fl / max(it, 1), iterations_per_step=it / steps)
+
     def control(self, ctrl, sys, k, state):
         u = np.zeros(self.ne)
         lib().orc_control(self.h, C.byref(ctrl), C.c_int(sys), C.c_int(k), _p(_f64(state)), _p(u))

@@ -4,6 +4,7 @@
 #pragma once
 #include <cmath>
 #include <vector>
+#include "orc_math.hpp"
 
 namespace orc {
 
@@ -17,6 +18,8 @@ inline double t_abs(double x) { return std::fabs(x); }
 inline long double t_abs(long double x) { return std::fabs(x); }
 inline double t_sqrt(double x) { return std::sqrt(x); }
 inline long double t_sqrt(long double x) { return std::sqrt(x); }
+inline Count t_abs(Count x) { return {std::fabs(x.v)}; }
+inline Count t_sqrt(Count x) { return sqrt(x); }
 #ifdef ORC_WITH_QUAD
 inline __float128 t_abs(__float128 x) { return x < 0 ? -x : x; }
 inline __float128 t_sqrt(__float128 x) {       // Newton on the double estimate: three steps reach binary128 accuracy
@@ -99,23 +102,23 @@ template <class T> inline void lu_solve(const T* LU, const int* piv, int n, T* B
 }
 
 // small dense inverse by Gauss-Jordan with partial pivoting (n <= 16); returns false on zero pivot
-inline bool small_inv(const double* A, double* Ai, int n) {
-    double W[16 * 32];
+template <class T> inline bool small_inv(const T* A, T* Ai, int n) {
+    T W[16 * 32];
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) { W[i * 2 * n + j] = A[i * n + j]; W[i * 2 * n + n + j] = (i == j) ? 1.0 : 0.0; }
+        for (int j = 0; j < n; j++) { W[i * 2 * n + j] = A[i * n + j]; W[i * 2 * n + n + j] = (i == j) ? T(1.0) : T(0.0); }
     for (int k = 0; k < n; k++) {
         int p = k;
-        double best = std::fabs(W[k * 2 * n + k]);
+        T best = t_abs(W[k * 2 * n + k]);
         for (int i = k + 1; i < n; i++)
-            if (std::fabs(W[i * 2 * n + k]) > best) { best = std::fabs(W[i * 2 * n + k]); p = i; }
-        if (best == 0.0) return false;
+            if (t_abs(W[i * 2 * n + k]) > best) { best = t_abs(W[i * 2 * n + k]); p = i; }
+        if (best == T(0.0)) return false;
         if (p != k) for (int j = 0; j < 2 * n; j++) std::swap(W[k * 2 * n + j], W[p * 2 * n + j]);
-        double inv = 1.0 / W[k * 2 * n + k];
+        T inv = T(1.0) / W[k * 2 * n + k];
         for (int j = 0; j < 2 * n; j++) W[k * 2 * n + j] *= inv;
         for (int i = 0; i < n; i++) {
             if (i == k) continue;
-            double l = W[i * 2 * n + k];
-            if (l == 0.0) continue;
+            T l = W[i * 2 * n + k];
+            if (l == T(0.0)) continue;
             for (int j = 0; j < 2 * n; j++) W[i * 2 * n + j] -= l * W[k * 2 * n + j];
         }
     }

@@ -31,6 +31,34 @@ inline double sqrt(double a) { return std::sqrt(a); }
 inline double val(double a) { return a; }
 inline double val(Dual a) { return a.v; }
 
+// ---------------------------------------------------------------- counting scalar
+// A double that counts the floating-point operations performed on it (per thread).  Instantiating the templated Newton solve with it
+// (oracle.cpp: orc_count_flops) gives the EXACT operation count of the literal algorithm -- residual, analytic KKT blocks, mixed-node block
+// LDU in dfs_list order, back-substitution, line search -- for one mechanism at one state: the "algorithmic flops" of SURVEY.md 8(d).
+// Convention: add/sub/mul/div/sqrt/compare of two Count values = 1 flop each (an FMA-capable machine executes a mul+add pair as one
+// instruction but it is 2 flops); negation and copies are free; products with an exact 0.0 or 1.0 constant still count (the literal code
+// performs them).
+struct FlopTally { long long add = 0, mul = 0, div = 0, sqrt_ = 0, cmp = 0; long long total() const { return add + mul + div + sqrt_; } };
+inline FlopTally& flop_tally() { static thread_local FlopTally t; return t; }
+struct Count {
+    double v;
+    Count() : v(0) {}
+    Count(double v_) : v(v_) {}
+};
+inline Count operator+(Count a, Count b) { flop_tally().add++; return {a.v + b.v}; }
+inline Count operator-(Count a, Count b) { flop_tally().add++; return {a.v - b.v}; }
+inline Count operator-(Count a) { return {-a.v}; }
+inline Count operator*(Count a, Count b) { flop_tally().mul++; return {a.v * b.v}; }
+inline Count operator/(Count a, Count b) { flop_tally().div++; return {a.v / b.v}; }
+inline Count& operator+=(Count& a, Count b) { a = a + b; return a; }
+inline Count& operator-=(Count& a, Count b) { a = a - b; return a; }
+inline Count& operator*=(Count& a, Count b) { a = a * b; return a; }
+inline bool operator==(Count a, Count b) { return a.v == b.v; }
+inline bool operator>(Count a, Count b) { flop_tally().cmp++; return a.v > b.v; }
+inline bool operator<(Count a, Count b) { flop_tally().cmp++; return a.v < b.v; }
+inline Count sqrt(Count a) { flop_tally().sqrt_++; return {std::sqrt(a.v)}; }
+inline double val(Count a) { return a.v; }
+
 // ---------------------------------------------------------------- 3-vectors / quaternions
 template <class T> struct V3 { T x, y, z; };
 template <class T> struct Q4 { T s, x, y, z; };

@@ -171,29 +171,29 @@ void body_dyn(double m, const double* J, double dt, double g, V3<T> v1, V3<T> w1
 }
 
 // 6x6 Jacobian d d / d(v2, w2) (row-major)
-inline void body_D(double m, const double* J, double dt, const double* w2, double* D) {
-    std::memset(D, 0, sizeof(double) * 36);
-    D[0] = D[7] = D[14] = m / dt;
-    double sq2 = std::sqrt(4.0 / (dt * dt) - (w2[0] * w2[0] + w2[1] * w2[1] + w2[2] * w2[2]));
-    double Jw[3] = {J[0] * w2[0] + J[1] * w2[1] + J[2] * w2[2], J[3] * w2[0] + J[4] * w2[1] + J[5] * w2[2],
-                    J[6] * w2[0] + J[7] * w2[1] + J[8] * w2[2]};
-    double W[9] = {0, -w2[2], w2[1], w2[2], 0, -w2[0], -w2[1], w2[0], 0};
-    double JW[9] = {0, -Jw[2], Jw[1], Jw[2], 0, -Jw[0], -Jw[1], Jw[0], 0};
+template <class T> inline void body_D(double m, const double* J, double dt, const T* w2, T* D) {
+    for (int i = 0; i < 36; i++) D[i] = T(0.0);
+    D[0] = D[7] = D[14] = T(m / dt);
+    T sq2 = sqrt(T(4.0 / (dt * dt)) - (w2[0] * w2[0] + w2[1] * w2[1] + w2[2] * w2[2]));
+    T Jw[3] = {T(J[0]) * w2[0] + T(J[1]) * w2[1] + T(J[2]) * w2[2], T(J[3]) * w2[0] + T(J[4]) * w2[1] + T(J[5]) * w2[2],
+               T(J[6]) * w2[0] + T(J[7]) * w2[1] + T(J[8]) * w2[2]};
+    T W[9] = {T(0.0), -w2[2], w2[1], w2[2], T(0.0), -w2[0], -w2[1], w2[0], T(0.0)};
+    T JW[9] = {T(0.0), -Jw[2], Jw[1], Jw[2], T(0.0), -Jw[0], -Jw[1], Jw[0], T(0.0)};
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
-            double wj = 0;
-            for (int k = 0; k < 3; k++) wj += W[i * 3 + k] * J[k * 3 + j];
-            D[(3 + i) * 6 + 3 + j] = sq2 * J[i * 3 + j] + wj - JW[i * 3 + j] - Jw[i] * w2[j] / sq2;
+            T wj = T(0.0);
+            for (int k = 0; k < 3; k++) wj += W[i * 3 + k] * T(J[k * 3 + j]);
+            D[(3 + i) * 6 + 3 + j] = sq2 * T(J[i * 3 + j]) + wj - JW[i * 3 + j] - Jw[i] * w2[j] / sq2;
         }
 }
 
 // T_w = V L(Omega)^T dOmega/dw2 = (dt^2/4) (w w^T / sq + sq I - [w]x)   (3x3)
-inline void T_omega(const double* w, double dt, double* Tm) {
-    double sq = std::sqrt(4.0 / (dt * dt) - (w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
-    double c = dt * dt / 4;
-    double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+template <class T> inline void T_omega(const T* w, double dt, T* Tm) {
+    T sq = sqrt(T(4.0 / (dt * dt)) - (w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+    T c = T(dt * dt / 4);
+    T W[9] = {T(0.0), -w[2], w[1], w[2], T(0.0), -w[0], -w[1], w[0], T(0.0)};
     for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) Tm[i * 3 + j] = c * (w[i] * w[j] / sq + (i == j ? sq : 0.0) - W[i * 3 + j]);
+        for (int j = 0; j < 3; j++) Tm[i * 3 + j] = c * (w[i] * w[j] / sq + (i == j ? sq : T(0.0)) - W[i * 3 + j]);
 }
 
 // 1-DoF joint input u -> body wrenches (SURVEY A.3 `setForce!`/`applyFtau!`): F world frame, tau body frame

@@ -181,3 +181,24 @@ def test_newton_count_is_rounding_marginal_at_default_eps(cc, orc):
     assert not out[1e-7][0].any()                                # away from the noise floor the count is well defined
     d, marg = out[1e-10]
     assert d.any() and d.max() <= 2 and np.all(d <= marg)        # at the default eps it is not, exactly where the oracle flags marginal decisions
+
+
+def test_counting_scalar_rollout_is_bit_identical_and_pins_the_flop_count(cc, orc):
+    """"exact count from the oracle instrumented with a counting scalar type".  The Newton solve of the oracle is templated on its
+    scalar; instantiated with orc::Count it performs the same operations in the same order (final states and iteration counts BIT-identical to
+    the Float64 instantiation) while tallying them.  bench.py uses this count as the algorithmic FP64 work of a sim step."""
+    from helpers import cartpole_states, oracle_lqr_gains
+    mech, cfg = cc.examples.cartpole()
+    B, steps = 4, 300
+    st0 = cartpole_states(cc, mech, B, seed=1)
+    o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=20.0)
+    co = o["om"].make_ctrl(B, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
+    r = o["om"].simulate(st0, steps, ctrl=co)
+    for s in range(B):
+        c = o["om"].count_flops_rollout(st0[s], steps, ctrl=co, sys=s)
+        assert np.array_equal(c["state"], r["states"][s]) and c["iterations"] == r["iters"][s]
+        # cartpole (2 bodies, 2 joints of 5 rows): 16.5 - 19 kflop per literal Newton iteration (residual x2, analytic blocks, mixed-node LDU, substitution)
+        assert 16.0e3 < c["flops_per_iteration"] < 19.5e3, c["flops_per_iteration"]
+        assert c["mul"] > c["add"] > 100 * c["div"] > 0 and c["sqrt"] > 0
+    one = o["om"].count_flops(st0[0])
+    assert one["iterations"] >= 1 and one["flops"] == one["add"] + one["mul"] + one["div"] + one["sqrt"]
