@@ -1,4 +1,6 @@
 // csrc/ccb_api.cu -- the extern "C" surface declared in include/ccb.h (handles, copies, launches).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "ccb_internal.h"
@@ -87,6 +89,8 @@ int ccb_batch_destroy(ccb_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->state); cudaFree(b->lambda); cudaFree(b->status_dev); cudaFree(b->storage_dev);
     if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    for (int i = 0; i < 2; i++) { if (b->ev_kernel[i]) cudaEventDestroy(b->ev_kernel[i]); if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]); }
     delete b;
     return CCB_OK;
 }
@@ -238,8 +242,8 @@ int ccb_ctrl_pid_state(ccb_ctrl* c, double* integrated, double* last, int32_t se
 }
 
 // ------------------------------------------------------------------------------------------------ simulate!
-int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage_dev,
-                        int32_t* status_dev) {
+static int simulate_launch(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage_dev, int32_t* status_dev,
+                           int status_accum) {
     if (!b || steps < 0) { set_error("ccb_simulate: bad arguments"); return CCB_E_INVALID; }
     if (ctrl && ctrl->device != b->device) { set_error("ccb_simulate: controller lives on another device"); return CCB_E_INVALID; }
     CCB_CUDA(cudaSetDevice(b->device));
@@ -266,10 +270,70 @@ int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps,
     SimArgs a;
     a.state = b->state; a.lambda = b->lambda; a.storage = storage_dev; a.status = status_dev;
     a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr; a.spw = opts ? opts->reserved : 0;
+    a.status_accum = status_accum;
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
     a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;
     return launch_rollout(*view, C, a, opts ? opts->lanes : 0, b->mech->h.lanes, b->stream);
+}
+
+int ccb_simulate_device(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage_dev,
+                        int32_t* status_dev) {
+    return simulate_launch(b, ctrl, k0, steps, opts, storage_dev, status_dev, 0);
+}
+
+// record = true with a HOST trajectory buffer [steps][B][nb][13] (104 nb bytes per system-step: 1.7 GB for 4096 cartpoles x 2000 steps, as
+// long on PCIe as the rollout itself).  The rollout is cut into chunks of steps (the kernels resume bit-exactly from the stored state,
+// multipliers, PID integrators and step index k0): chunk c computes into one half of a device double buffer while the copy stream drains
+// chunk c-1 from the other half -- one cudaMemcpyAsync per chunk, ordered by events.  The copy of a chunk is issued AFTER the next chunk's
+// launch, so the overlap also holds for pageable host memory (where the copy call blocks the host).  Device memory: 2 chunks, not the
+// whole trajectory.
+static size_t record_chunk_bytes() {
+    if (const char* e = getenv("CCB_RECORD_CHUNK_MB")) return (size_t)std::max(1, atoi(e)) << 20;
+    return (size_t)64 << 20;
+}
+static int simulate_record_pipelined(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage, size_t per_step) {
+    const size_t step_bytes = per_step * sizeof(double);
+    const size_t target = record_chunk_bytes();
+    int chunk = (int)std::min<size_t>((size_t)steps, std::max<size_t>(8, target / step_bytes));
+    const int nchunks = (steps + chunk - 1) / chunk;
+    const size_t need = 2 * (size_t)chunk * step_bytes;
+    if (b->storage_cap < need) {
+        cudaFree(b->storage_dev); b->storage_dev = nullptr; b->storage_cap = 0;
+        cudaError_t e = cudaMalloc(&b->storage_dev, need);
+        if (e != cudaSuccess) { b->storage_dev = nullptr; return cuda_fail(e, "cudaMalloc(storage chunks)"); }
+        b->storage_cap = need;
+    }
+    if (!b->copy_stream) {
+        CCB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CCB_CUDA(cudaEventCreateWithFlags(&b->ev_kernel[i], cudaEventDisableTiming));
+            CCB_CUDA(cudaEventCreateWithFlags(&b->ev_copy[i], cudaEventDisableTiming));
+        }
+    }
+    auto drain = [&](int c) -> int {            // D2H of chunk c behind its kernel
+        const int buf = c & 1, s0 = c * chunk, sc = std::min(chunk, steps - s0);
+        CCB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_kernel[buf], 0));
+        CCB_CUDA(cudaMemcpyAsync(storage + (size_t)s0 * per_step, b->storage_dev + (size_t)buf * chunk * per_step, (size_t)sc * step_bytes, cudaMemcpyDeviceToHost,
+                                 b->copy_stream));
+        CCB_CUDA(cudaEventRecord(b->ev_copy[buf], b->copy_stream));
+        return CCB_OK;
+    };
+    int rc = CCB_OK;
+    for (int c = 0; c < nchunks && rc == CCB_OK; c++) {
+        const int buf = c & 1, s0 = c * chunk, sc = std::min(chunk, steps - s0);
+        if (c >= 2) CCB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy[buf], 0));      // the half is free again
+        rc = simulate_launch(b, ctrl, k0 + s0, sc, opts, b->storage_dev + (size_t)buf * chunk * per_step, b->status_dev, c > 0);
+        if (rc != CCB_OK) break;
+        CCB_CUDA(cudaEventRecord(b->ev_kernel[buf], b->stream));
+        if (c >= 1) rc = drain(c - 1);
+    }
+    if (rc == CCB_OK) rc = drain(nchunks - 1);
+    cudaError_t e1 = cudaStreamSynchronize(b->copy_stream), e2 = cudaStreamSynchronize(b->stream);
+    if (rc != CCB_OK) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "record pipeline (copy stream)");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "record pipeline (compute stream)");
+    return CCB_OK;
 }
 
 int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const ccb_sim_opts* opts, double* storage, int32_t* status) {
@@ -277,6 +341,13 @@ int ccb_simulate(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t steps, const 
     CCB_CUDA(cudaSetDevice(b->device));
     const size_t per_step = (size_t)b->B * b->mech->h.nb * 13;
     double* sdev = nullptr;
+    if (storage && steps > 16 && per_step * steps * sizeof(double) >= 2 * record_chunk_bytes() && !getenv("CCB_RECORD_NO_PIPELINE")) {
+        int rc = simulate_record_pipelined(b, ctrl, k0, steps, opts, storage, per_step);
+        if (rc != CCB_OK) return rc;
+        if (status) CCB_CUDA(cudaMemcpyAsync(status, b->status_dev, (size_t)b->B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CCB_CUDA(cudaStreamSynchronize(b->stream));
+        return CCB_OK;
+    }
     if (storage && steps > 0) {
         const size_t need = per_step * steps * sizeof(double);
         if (b->storage_cap < need) {

@@ -137,7 +137,19 @@ struct SimArgs {
     int knot_input;     // 1: `state` already holds the knot (x2,q2,v1,w1) of a setpoint; one Newton solve, state untouched (linearsystem)
     double* s_out;      // [B][nb][6] solution (v2,w2) when knot_input
     int spw;            // chain kernel: systems per warp (0 = automatic)
+    int status_accum;   // 1: this launch continues a rollout split over several launches: fold its counts into what `status` already holds
 };
+
+// status[s] = total Newton iterations of the rollout, negated if any step failed (0: failed before the first iteration); a continuing
+// launch (status_accum) adds to the earlier launches' count and keeps their failure flag
+__device__ __forceinline__ void write_status(const SimArgs& A, int sys, int total, bool failed) {
+    if (A.status_accum) {
+        const int o = A.status[sys];
+        if (o <= 0) failed = true;
+        total += o < 0 ? -o : o;
+    }
+    A.status[sys] = failed ? -total : total;
+}
 
 // lanes: 0 = automatic (row-per-lane kernel K1r for short serial chains, else the chain kernel K1c for serial chains, else the
 // multi-warp rows kernel K1m for longer serial chains, else the general kernel K1 with default_lanes), 5 = force K1r, 6 = force K1m,
@@ -172,6 +184,9 @@ struct ccb_batch {
     cudaStream_t stream = nullptr;
     double* storage_dev = nullptr; size_t storage_cap = 0;
     int* status_dev = nullptr;
+    // record = true pipeline (ccb_simulate): device double buffer of trajectory chunks, drained by a copy stream while the next chunk computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_kernel[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 };
 struct ccb_ctrl {
     ccb::DevCtrl v;

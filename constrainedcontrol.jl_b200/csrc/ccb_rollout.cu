@@ -506,11 +506,11 @@ template <int G> __global__ void __launch_bounds__(32) rollout_kernel(const DevM
     if (valid && A.knot_input) {
         for (int i = lane; i < 6 * M.nb; i += G) A.s_out[(size_t)sys * 6 * M.nb + i] = m.s[i];
         for (int i = lane; i < M.ml; i += G) A.lambda[(size_t)sys * M.ml + i] = m.lam[i];
-        if (A.status && lane == 0) A.status[sys] = failed ? -total_iters : total_iters;
+        if (A.status && lane == 0) write_status(A, sys, total_iters, failed);
     } else if (valid) {
         for (int i = lane; i < nst; i += G) A.state[(size_t)sys * nst + i] = m.z[i];
         for (int i = lane; i < M.ml; i += G) A.lambda[(size_t)sys * M.ml + i] = m.lam[i];
-        if (A.status && lane == 0) A.status[sys] = failed ? -total_iters : total_iters;
+        if (A.status && lane == 0) write_status(A, sys, total_iters, failed);
     }
 }
 

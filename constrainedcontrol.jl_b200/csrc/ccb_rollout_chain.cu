@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(32) rollout_chain_kernel(const DevMech M, cons
         for (int i = 0; i < 13; i++) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
         for (int r = 0; r < dim; r++) A.lambda[(size_t)sys * M.ml + r0 + r] = lam[r];
     }
-    if (valid && A.status && j == 0) A.status[sys] = anyfail > 0.0 ? -total_iters : total_iters;
+    if (valid && A.status && j == 0) write_status(A, sys, total_iters, anyfail > 0.0);
 }
 
 }  // namespace

@@ -619,7 +619,7 @@ __global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCt
             if (i % 5 == r) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     }
-    if (A.status && q == 0) A.status[sys] = failed ? -total_iters : total_iters;
+    if (A.status && q == 0) write_status(A, sys, total_iters, failed);
 }
 
 }  // namespace

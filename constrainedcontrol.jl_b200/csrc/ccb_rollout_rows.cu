@@ -53,7 +53,9 @@ __device__ __forceinline__ double rcp_fast(double x) {
 #endif
 }
 
-template <int NJ>
+// GEN: false = the LQR-family instantiation (no controller, LQR Inf / finite, TrackingLQR): the PID and open-loop-table code (joint coordinate,
+// atan2, integrator state) is compiled out, which shortens the hot loop's SASS and frees registers; true = every law.
+template <int NJ, bool GEN>
 __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
     extern __shared__ __align__(16) double smem[];
     constexpr int G = 5 * NJ, SPW = 32 / G;
@@ -143,7 +145,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
         }
         // ---------------- control!(k) part 1: laws that read the continuous state (PID), open-loop tables
         double u = 0.0;
-        if (C.kind == CCB_CTRL_PID || C.kind == CCB_CTRL_TABLE) {
+        if (GEN && (C.kind == CCB_CTRL_PID || C.kind == CCB_CTRL_TABLE)) {
             double pz[7];
 #pragma unroll
             for (int i = 0; i < 7; i++) pz[i] = shfl_d(z[i], plane);
@@ -577,7 +579,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             if (i % 5 == r) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     }
-    if (valid && A.status && q == 0) A.status[sys] = failed ? -total_iters : total_iters;
+    if (valid && A.status && q == 0) write_status(A, sys, total_iters, failed);
 }
 
 }  // namespace
@@ -590,14 +592,20 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cu
     const int G = 5 * M.nj, spw = 32 / G;
     const int grid = (a.B + spw - 1) / spw;
     const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
+    const bool gen = C.kind == CCB_CTRL_PID || C.kind == CCB_CTRL_TABLE;
+#define K1R_LAUNCH(NJ_)                                                                          \
+    case NJ_:                                                                                    \
+        if (gen) rollout_rows_kernel<NJ_, true><<<grid, 32, smem, stream>>>(M, C, a, ord);       \
+        else rollout_rows_kernel<NJ_, false><<<grid, 32, smem, stream>>>(M, C, a, ord);          \
+        break;
     switch (M.nj) {
-        case 1: rollout_rows_kernel<1><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
-        case 2: rollout_rows_kernel<2><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
-        case 3: rollout_rows_kernel<3><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
-        case 4: rollout_rows_kernel<4><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
-        case 5: rollout_rows_kernel<5><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
-        default: rollout_rows_kernel<6><<<grid, 32, smem, stream>>>(M, C, a, ord); break;
+        K1R_LAUNCH(1) K1R_LAUNCH(2) K1R_LAUNCH(3) K1R_LAUNCH(4) K1R_LAUNCH(5)
+        default:
+            if (gen) rollout_rows_kernel<6, true><<<grid, 32, smem, stream>>>(M, C, a, ord);
+            else rollout_rows_kernel<6, false><<<grid, 32, smem, stream>>>(M, C, a, ord);
+            break;
     }
+#undef K1R_LAUNCH
     g_launches++;
     CCB_CUDA(cudaGetLastError());
     return CCB_OK;

@@ -103,7 +103,9 @@ def _worker_peer_failure(rank, world, port, fail_rank, q):
 
     try:
         cc.dist._peer_fill(t, 0, 128, run_shard)
+        cc.dist._peer_fill(t, 0, 128, lambda tables: log.append(f"refill:{len(tables)}"))      # re-fill: no second allocation / mapping
         outcome = "ok"
+        cc.dist._peer_unmap(t)
     except cc.dist.PeerProtocolError as e:
         outcome = "local" if "synthesis failed" in str(e) else "peer"
     q.put((rank, outcome, list(log), t.ptr is None))
@@ -126,7 +128,7 @@ def test_peer_protocol_failure_reaches_every_rank_world2(fail_rank):
         p.join(timeout=60)
     if fail_rank < 0:
         assert [r[1] for r in res] == ["ok", "ok"]
-        assert all(r[2] == ["alloc", "open", "shard:2", "close"] and not r[3] for r in res)
+        assert all(r[2] == ["alloc", "open", "shard:2", "refill:2", "close"] and not r[3] for r in res)
     else:
         assert [r[1] for r in res] == ["peer", "local"]
         assert all(r[2] == ["alloc", "open", "shard:2", "close", "free"] and r[3] for r in res)

@@ -123,3 +123,32 @@ def test_peer_gain_tables_two_ranks(cc):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("table == gathered: True") == 2
+
+
+def test_record_pipeline_is_bit_identical_to_one_launch(cc, monkeypatch):
+    """ccb_simulate with a host trajectory buffer cuts the rollout into chunks (device double buffer drained by a copy stream while the next chunk
+    computes).  The kernels resume from the stored state / multipliers / PID integrators / step index, so the recorded trajectory, the final
+    state and the per-system Newton counts (accumulated over the launches) equal those of ONE launch bit for bit -- LQR (finite horizon: the
+    `k < N` gate crosses a chunk boundary) and PID (persistent integrator)."""
+    mech, cfg = cc.examples.cartpole()
+    B, steps = 300, 260
+    st0 = cartpole_states(cc, mech, B, seed=5)
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], 2.0, xd=cfg["xd"])      # N = 200 < steps
+    mech2, cfg2 = cc.examples.doublependulum()
+    goals = np.stack([np.linspace(-1, 1, 64), np.linspace(1, -1, 64)], axis=1)
+    out = {}
+    for mode in ("one", "chunks"):
+        if mode == "one":
+            monkeypatch.setenv("CCB_RECORD_NO_PIPELINE", "1")
+        else:
+            monkeypatch.delenv("CCB_RECORD_NO_PIPELINE")
+            monkeypatch.setenv("CCB_RECORD_CHUNK_MB", "1")       # 1 MB chunks: 16 steps of the cartpole batch, 78 of the pendulum batch
+        sto, fin, status = cc.simulate(mech, steps * mech.dt, lqr, record=True, states=st0, return_status=True)
+        pid = cc.PID(mech2, cfg2["eqcids"], goals, P=cfg2["P"], I=cfg2["I"], D=cfg2["D"])
+        sto2, fin2, status2 = cc.simulate(mech2, 4.0, pid, record=True, states=mech2.batch_states(64), return_status=True)
+        out[mode] = (sto.data.copy(), fin, status, sto2.data.copy(), fin2, status2, pid.pid_state(64))
+    a, b = out["one"], out["chunks"]
+    for x, y in zip(a[:6], b[:6]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[6][0], b[6][0]) and np.array_equal(a[6][1], b[6][1])
+    assert np.all(a[2] > 0) and np.all(a[5] != 0)
