@@ -50,9 +50,38 @@ def parse_urdf(path: str) -> dict:
     return dict(links=links, joints=joints)
 
 
+def drop_massless_frames(desc: dict) -> dict:
+    """Links without an <inertial> element (camera / wrist / mounting FRAMES such as right_hand_camera, right_wrist, head_camera,
+    controller_box, pedestal_feet of examples/examples_files/sawyer.urdf) that hang on a fixed joint and carry no further links are not
+    bodies: with m = 0 and J = 0 their 6x6 dynamics block is identically zero and the maximal-coordinate KKT system is singular (in the
+    reference as much as here).  The same holds for the file's placeholder links (right_hand, right_l1_2, right_l2_2, right_l4_2: m = 1e-8 kg
+    and an inertia "tensor" with all nine entries 1e-8 -- rank 1, not a physical inertia: the rotational pivot block of the tree-ordered
+    LDU is singular).  Both kinds are removed together with their fixed joint (their 1e-8 kg are below the rounding of the 1-5 kg links they
+    are welded to); such a link on a movable joint, or with links depending on it, is an error."""
+    links = list(desc["links"]); joints = list(desc["joints"])
+    changed = True
+    while changed:
+        changed = False
+        parents = {j["parent"] for j in joints}
+        for l in links:
+            J = np.array(l["inertia"], dtype=float)
+            ev = np.linalg.eigvalsh(0.5 * (J + J.T))
+            massless = (l["mass"] == 0.0 and not np.any(J)) or (np.any(J) and ev.min() <= 1e-9 * ev.max())
+            jin = [j for j in joints if j["child"] == l["name"]]
+            if massless and jin and l["name"] not in parents:
+                if any(j["type"] != "fixed" for j in jin):
+                    raise ValueError(f"URDF link {l['name']} has no inertia but hangs on a movable joint")
+                links = [x for x in links if x is not l]
+                joints = [j for j in joints if j["child"] != l["name"]]
+                changed = True
+                break
+    return dict(links=links, joints=joints)
+
+
 def mechanism_from_description(desc: dict, floating: bool = False, g: float = -9.81, dt: float = 0.01) -> Mechanism:
     if floating:
         raise NotImplementedError("floating bases are outside the hot-path scope")
+    desc = drop_massless_frames(desc)
     links = {l["name"]: l for l in desc["links"]}
     children = {j["child"] for j in desc["joints"]}
     roots = [l["name"] for l in desc["links"] if l["name"] not in children]

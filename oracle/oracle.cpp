@@ -252,7 +252,7 @@ bool solve_sparse(const Mech& M, WorkT<T>& W) {
     for (int i = 0; i < N; i++) {
         const int c = M.dfs_list[i] - 1, dc = M.node_dim[c];
         T* Dinv = W.dinv.data() + W.dinv_off[c];
-        if (!small_inv(B(c, c), Dinv, dc)) return false;
+        if (!small_inv(B(c, c), Dinv, dc)) { if (getenv("ORC_DEBUG")) fprintf(stderr, "solve_sparse: singular pivot block at dfs position %d (node id %d, dim %d)\n", i, c + 1, dc); return false; }
         const std::vector<int>& lat = W.later[i];
         for (int p : lat) {
             const int dp = M.node_dim[p];

@@ -22,3 +22,7 @@ json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_arm.json"), "w")
 # the branching Sawyer description with fixed joints (reference examples/examples_files/sawyer_simple.urdf): SURVEY 8(f) n3
 desc = cc.urdf.parse_urdf("/root/reference/examples/examples_files/sawyer_simple.urdf")
 json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_simple.json"), "w"), indent=1)
+
+# the full Sawyer description (reference examples/examples_files/sawyer.urdf: 24 links, 23 joints, massless camera / wrist frames): SURVEY 8(f) n3
+desc = cc.urdf.parse_urdf("/root/reference/examples/examples_files/sawyer.urdf")
+json.dump(desc, open(__file__.replace("make_golden.py", "sawyer_full.json"), "w"), indent=1)

@@ -361,3 +361,54 @@ def test_c4_sawyer_pid_and_infinite_horizon_lqr_on_the_long_chain_kernel(cc, orc
     r = om.simulate(st1, 100, ctrl=co, record=True, nthreads=5)
     sto, fin, status = cc.simulate(mech, 1.0, lqr, record=True, states=st1, return_status=True)
     assert np.all(status > 0) and rel_err(sto.data, r["storage"]) < TOL
+
+
+def test_sawyer_full_urdf(cc, orc):
+    """SURVEY 8(f) n3, the FULL examples/examples_files/sawyer.urdf (24 links, 23 joints): after the massless frames and the rank-1-inertia
+    placeholder links are dropped (urdf.drop_massless_frames) 14 bodies / 14 joints remain -- pedestal, arm base and torso welded to the origin,
+    head + screen and two cable-guide bodies branching off the arm (6 six-row Fixed joints, 8 revolute joints, 76 constraint rows)."""
+    mech = cc.urdf.mechanism_from_json(os.path.join(GOLD, "sawyer_full.json"), floating=False, g=-9.81, dt=0.01)
+    assert (mech.nb, mech.ne, mech.ml) == (14, 14, 76)
+    g = cc.handle(mech).graph()
+    om = orc.OracleMech(mech.desc())
+    go = om.graph()
+    for k in go:
+        assert np.array_equal(g[k], go[k]), k                                  # ids, dfs_list, parents: bit-exact
+    assert len(g["loop_edges"]) == 0
+    names = {e.name: i for i, e in enumerate(mech.eqconstraints)}
+    B = 5
+    rng = np.random.default_rng(21)
+    st0 = np.zeros((B, mech.nb, 13))
+    for s in range(B):
+        cc.urdf.zero_configuration(mech, {names[f"right_j{j}"]: rng.uniform(-0.3, 0.3) for j in range(7)} | {names["head_pan"]: rng.uniform(-0.5, 0.5)})
+        st0[s] = mech.state_vector()
+    cc.urdf.zero_configuration(mech)
+    assert constraint_violation(cc, mech, st0) < 1e-12
+    # the arm falls under gravity (uncontrolled), general kernel K1
+    r = om.simulate(st0, 80, record=True, nthreads=5)
+    sto, fin, status = cc.simulate(mech, 0.8, None, record=True, states=st0, return_status=True)
+    assert np.all(status > 0) and np.all(r["iters"] > 0)
+    assert rel_err(sto.data, r["storage"]) < TOL
+    assert constraint_violation(cc, mech, fin) < 1e-9
+    ped = [i for i, b in enumerate(mech.bodies) if b.name == "pedestal"][0]
+    assert np.abs(fin[:, ped, 0:3] - st0[:, ped, 0:3]).max() < 1e-12           # welded to the origin
+    # LQR about the zero configuration with gravity compensation from the linearisation's own multipliers is out of the example set;
+    # PID on three arm joints and the head while the rest swings (pid.jl:69-88)
+    ids = [mech.eqconstraints[names[n]].id for n in ("right_j0", "right_j3", "head_pan")]
+    eqc = [mech.eqc_index(i) for i in ids]
+    P, I, D = [60.0, 20.0, 2.0], [1.0, 0.5, 0.0], [10.0, 3.0, 0.3]
+    goal = np.tile([0.2, -0.1, 0.4], (B, 1))
+    integ = np.zeros((B, 3)); last = np.zeros((B, 3))
+    co = om.make_ctrl(B, kind="pid", eqc=eqc, P=P, I=I, D=D, goal=goal, pid_int=integ, pid_last=last)
+    r2 = om.simulate(st0, 60, ctrl=co, record=True, nthreads=5)
+    pid = cc.PID(mech, ids, goal, P=P, I=I, D=D)
+    sto2, fin2, status2 = cc.simulate(mech, 0.6, pid, record=True, states=st0, return_status=True)
+    assert np.all(status2 > 0) and np.all(r2["iters"] > 0)
+    assert rel_err(sto2.data, r2["storage"]) < 1e-8
+    # linearsystem of the whole robot at the zero configuration (n = 168): block-sparse K2 vs the oracle's whole-residual AD
+    zd = mech.state_vector()
+    A, Bu, Bl, G = cc.linearsystem(mech, zd, np.zeros(len(eqc)), eqc)
+    lo = om.linearize(zd, np.zeros(len(eqc)), eqc)
+    assert A.shape == (1, 168, 168)
+    for mine, ref in ((A[0], lo["A"]), (Bu[0], lo["Bu"]), (G[0], lo["G"])):
+        assert rel_err(mine, ref) < TOL

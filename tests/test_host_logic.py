@@ -102,3 +102,37 @@ def test_deltabot_initial_condition_grid_matches_the_example(cc):
     mech.set_state_vector(nominal)
     assert worst < 1e-12
     assert np.unique(st.reshape(2048, -1), axis=0).shape[0] == 2048
+
+
+def test_full_sawyer_urdf_ingestion_rules():
+    """host logic of SURVEY 8(f) n3 (no GPU): the full sawyer.urdf description (tests/golden/sawyer_full.json, numbers parsed from the reference's
+    file) loses its massless frames and its rank-1-inertia placeholder links, keeps document order, and rejects descriptions it cannot represent"""
+    import json, os
+    import numpy as np
+    import ccb200 as cc
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sawyer_full.json")
+    desc = json.load(open(gold))
+    assert len(desc["links"]) == 24 and len(desc["joints"]) == 23
+    kept = cc.urdf.drop_massless_frames(desc)
+    dropped = {l["name"] for l in desc["links"]} - {l["name"] for l in kept["links"]}
+    assert dropped == {"controller_box", "pedestal_feet", "right_hand_camera", "right_wrist", "head_camera", "right_hand", "right_l1_2", "right_l2_2", "right_l4_2"}
+    assert [l["name"] for l in kept["links"]] == [l["name"] for l in desc["links"] if l["name"] not in dropped]        # document order kept
+    assert all(j["type"] == "fixed" for j in desc["joints"] if j["child"] in dropped)
+    mech = cc.urdf.mechanism_from_description(desc, floating=False, g=-9.81)
+    assert (mech.nb, mech.ne, mech.ml) == (14, 14, 76)
+    assert [e.name for e in mech.eqconstraints][:4] == ["pedestal_fixed", "right_arm_mount", "torso_t0", "right_j0"]
+    assert abs(np.abs(mech.constraint_values()).max()) < 1e-12                 # the zero configuration satisfies every joint
+    # a massless link on a movable joint cannot be represented in maximal coordinates: refused, not silently dropped
+    bad = json.loads(json.dumps(desc))
+    for j in bad["joints"]:
+        if j["child"] == "right_wrist":
+            j["type"] = "revolute"
+    try:
+        cc.urdf.drop_massless_frames(bad)
+        assert False, "expected ValueError"
+    except ValueError as e:
+        assert "right_wrist" in str(e)
+    # the descriptions used elsewhere are untouched by the rule
+    for name, dims in (("sawyer_simple.json", (10, 10, 52)), ("sawyer_arm.json", (7, 7, 35))):
+        m = cc.urdf.mechanism_from_json(os.path.join(os.path.dirname(gold), name), floating=False, g=0.0)
+        assert (m.nb, m.ne, m.ml) == dims
