@@ -13,6 +13,19 @@ size_t riccati_project_ws_doubles(int n, int nu, int ml);
 size_t riccati_sweep_ws_doubles(int n, int nu);
 int riccati_project_device(int P, int n, int nu, int ml, const double* A, const double* Bu, const double* Bl, const double* G, double* At, double* D,
                            double* ws, cudaStream_t stream);
+int riccati_project_mech_device(const DevMech& M, int P, int nu, const double* A, const double* Bu, const double* Bl, const double* G, double* At,
+                                double* D, cudaStream_t stream);
+// projection of P linearisations of mechanism H: the structure-aware kernel (ccb_riccati_project.cu) when it applies, else the dense one
+static int project_linearisations(HostMech* H, int device, int P, int nu, const double* A, const double* Bu, const double* Bl, const double* G, double* At,
+                                  double* D, double* ws, cudaStream_t stream) {
+    const DevMech* view;
+    int rc = get_dev_mech(H, device, &view);
+    if (rc != CCB_OK) return rc;
+    rc = riccati_project_mech_device(*view, P, nu, A, Bu, Bl, G, At, D, stream);
+    if (rc == 1) rc = riccati_project_device(P, 12 * H->nb, nu, H->ml, A, Bu, Bl, G, At, D, ws, stream);
+    return rc;
+}
+
 int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const double* D, long long stride_t_A, long long stride_t_D,
                          long long stride_s_A, long long stride_s_D, const double* Q, long long Q_bs, const double* R, long long R_bs, double* Ku,
                          int* kexit, int* iters, double* ws, cudaStream_t stream, int k_hi = 0, int k_lo = 0, int resume = 0);
@@ -274,7 +287,7 @@ static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, co
     pt.mark(0);
     if ((rc = linearize_device(&m->h, device, S, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0)) != CCB_OK) return bail(rc);
     pt.mark(1);
-    if ((rc = riccati_project_device(S, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0)) != CCB_OK) return bail(rc);
+    if ((rc = project_linearisations(&m->h, device, S, nu, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0)) != CCB_OK) return bail(rc);
     pt.mark(2);
     if ((rc = riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2,
                                    0)) != CCB_OK) return bail(rc);
@@ -602,7 +615,7 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
             pt.mark(0);
             CCB_TRY(linearize_device(&m->h, device, Pc, d_zd, d_Fd, d_eqc, nu, opts, d_A, d_Bu, d_Bl, d_G, d_lam, d_s, d_status, 0));
             pt.mark(1);
-            CCB_TRY(riccati_project_device(Pc, n, nu, ml, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
+            CCB_TRY(project_linearisations(&m->h, device, Pc, nu, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0));
             pt.mark(2);
             CCB_TRY(riccati_sweep_device(cs, n, nu, N, d_At, d_D, (long long)n * n, (long long)n * nu, (long long)N * n * n, (long long)N * n * nu, d_Q, 0, d_R,
                                          0, Kdst, d_kexit, d_iters, d_ws2, 0));
@@ -646,8 +659,8 @@ static int tracking_synth_device(ccb_mech* m, int device, int S, int N, const do
                                       d_Bl + off * n * ml, d_G + off * ml * n, d_lam + off * ml, d_s + off * nb * 6, d_status + off, sa);
                 if (rc != CCB_OK) break;
                 cudaEventRecord(e5[1], sa);
-                rc = riccati_project_device(Pb, n, nu, ml, d_A + off * n * n, d_Bu + off * n * nu, d_Bl + off * n * ml, d_G + off * ml * n, d_At + off * n * n,
-                                            d_D + off * n * nu, d_ws1 + off * riccati_project_ws_doubles(n, nu, ml), sa);
+                rc = project_linearisations(&m->h, device, Pb, nu, d_A + off * n * n, d_Bu + off * n * nu, d_Bl + off * n * ml, d_G + off * ml * n,
+                                            d_At + off * n * n, d_D + off * n * nu, d_ws1 + off * riccati_project_ws_doubles(n, nu, ml), sa);
                 if (rc != CCB_OK) break;
                 cudaEventRecord(e5[2], sa);
                 cudaStreamWaitEvent(sb, e5[2], 0);
