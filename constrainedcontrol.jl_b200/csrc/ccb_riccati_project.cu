@@ -23,14 +23,17 @@ namespace {
 
 constexpr int PT = 128;   // threads per CTA
 
-template <int MLMAX>
-__global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_kernel(const DevMech Mv, int n, int nu, int ml, int ldm, int ldy, const double* __restrict__ A,
+// MLMAX: compile-time bound of mλ (the substitution is straight-line code over MLMAX rows with the right-hand side in registers; the LU
+// factors are padded with an identity to MLMAX x MLMAX so that no guard is needed); MINB: CTAs per SM the register budget is set for.
+template <int MLMAX, int MINB>
+__global__ void __launch_bounds__(PT, MINB) riccati_project_mech_kernel(const DevMech Mv, int n, int nu, int ml, int ldm, int ldy, const double* __restrict__ A,
                                                                    const double* __restrict__ Bu, const double* __restrict__ Bl,
                                                                    const double* __restrict__ G, double* __restrict__ At, double* __restrict__ D) {
     extern __shared__ __align__(16) double sm[];
-    double* Ms = sm;                              // [ml][ldm]   G Bλ, then its LU factors (unit lower | upper)
-    double* Y = Ms + (size_t)ml * ldm;            // [ml][ldy]   G [A | Bu], then (G Bλ)^-1 G [A | Bu]
+    double* Ms = sm;                              // [MLMAX][ldm] G Bλ, then its LU factors (unit lower | upper), identity beyond mλ
+    double* Y = Ms + (size_t)MLMAX * ldm;         // [ml][ldy]   G [A | Bu], then (G Bλ)^-1 G [A | Bu]
     double* Gc = Y + (size_t)ml * ldy;            // [ml][24]    row r of G on the parent block | child block of its joint
+    Gc += (Gc - sm) & 1;                          // 16-byte aligned: phase 3 reads the Bλ blocks as double2
     double* Bc = Gc + (size_t)ml * 24;            // [ml][24]    column r of Bλ on the same two blocks
     int* rb = reinterpret_cast<int*>(Bc + (size_t)ml * 24);   // [ml][2] parent / child body of the row's joint (-1: origin)
     int* piv = rb + 2 * ml;                       // [ml]
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_k
     A += p * n * n; Bu += p * n * nu; Bl += p * n * ml; G += p * ml * n; At += p * n * n; D += p * n * nu;
     const int W = n + nu;
 
+    for (int e = tid; e < MLMAX * ldm; e += PT) { const int i = e / ldm, c = e - ldm * i; Ms[e] = (i == c && i >= ml) ? 1.0 : 0.0; }
     for (int r = tid; r < ml; r += PT) {
         const int jt = __ldg(Mv.row_joint + r);
         rb[2 * r] = __ldg(Mv.j_parent + jt);
@@ -52,38 +56,44 @@ __global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_k
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ---- M = G Bλ from the compact blocks
-        for (int e = lane; e < ml * ml; e += 32) {
-            const int r = e / ml, c = e - ml * r;
-            double acc = 0.0;
+    // ---- M = G Bλ from the compact blocks: all threads (it used to be warp 0's job: a third of the serial chain the other warps wait for)
+    for (int e = tid; e < ml * ml; e += PT) {
+        const int r = e / ml, c = e - ml * r;
+        double acc = 0.0;
 #pragma unroll
-            for (int a = 0; a < 2; a++) {
-                const int ba = rb[2 * r + a];
-                if (ba < 0) continue;
+        for (int a = 0; a < 2; a++) {
+            const int ba = rb[2 * r + a];
+            if (ba < 0) continue;
 #pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    if (rb[2 * c + b] != ba) continue;
-                    const double* g = Gc + r * 24 + 12 * a;
-                    const double* bl = Bc + c * 24 + 12 * b;
+            for (int b = 0; b < 2; b++) {
+                if (rb[2 * c + b] != ba) continue;
+                const double2* g = reinterpret_cast<const double2*>(Gc + r * 24 + 12 * a);
+                const double2* bl = reinterpret_cast<const double2*>(Bc + c * 24 + 12 * b);
 #pragma unroll
-                    for (int k = 0; k < 12; k++) acc = fma(g[k], bl[k], acc);
-                }
+                for (int k = 0; k < 6; k++) { const double2 g2 = g[k], b2 = bl[k]; acc = fma(g2.x, b2.x, acc); acc = fma(g2.y, b2.y, acc); }
             }
-            Ms[(size_t)r * ldm + c] = acc;
         }
-        __syncwarp();
+        Ms[(size_t)r * ldm + c] = acc;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
         // ---- LU with partial pivoting (first row of largest magnitude), in place
         for (int k = 0; k < ml; k++) {
-            double best = -1.0;
+            // partial pivoting: the first row of largest magnitude.  |v| >= 0 orders like its bit pattern, so the warp-wide maximum is two
+            // 32-bit REDUX maxima (high, low word) and a REDUX minimum over the row indices instead of a five-round shuffle butterfly (10 dependent shuffles per pivot)
+            unsigned long long key = 0ull;
             int bi = k;
-            for (int i = k + lane; i < ml; i += 32) { const double v = fabs(Ms[(size_t)i * ldm + k]); if (v > best) { best = v; bi = i; } }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            for (int i = k + lane; i < ml; i += 32) {
+                const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(Ms[(size_t)i * ldm + k]));
+                if (i == k + lane || v > key) { key = v; bi = i; }
             }
+            const bool has = k + lane < ml;
+            const unsigned hi = has ? (unsigned)(key >> 32) : 0u;
+            const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (has && hi == mhi) ? (unsigned)key : 0u;
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+            bi = (int)__reduce_min_sync(0xffffffffu, (has && hi == mhi && lo == mlo) ? (unsigned)bi : 0xffffffffu);     // first such row
             if (lane == 0) piv[k] = bi;
             if (bi != k)
                 for (int c = lane; c < ml; c += 32) { const double t = Ms[(size_t)k * ldm + c]; Ms[(size_t)k * ldm + c] = Ms[(size_t)bi * ldm + c]; Ms[(size_t)bi * ldm + c] = t; }
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_k
                 double* ri = Ms + (size_t)i * ldm;
                 const double l = ri[k] * inv;
                 ri[k] = l;
+#pragma unroll 4
                 for (int c = k + 1; c < ml; c++) ri[c] = fma(-l, rk[c], ri[c]);
             }
             __syncwarp();
@@ -134,29 +145,24 @@ __global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_k
         double y[MLMAX];
 #pragma unroll
         for (int i = 0; i < MLMAX; i++) y[i] = i < ml ? Y[(size_t)i * ldy + j] : 0.0;
-        // constant trip counts everywhere so that the loops unroll completely and y[] stays in registers (a triangular inner bound left
-        // y[] in local memory for MLMAX = 40); rows / columns beyond ml multiply exact zeros of y and are skipped by the uniform guards
+        // straight-line code: the factors are padded with an identity, rows / columns beyond mλ contribute exact zeros
 #pragma unroll
         for (int i = 1; i < MLMAX; i++) {
-            if (i < ml) {
-                const double* ri = Ms + (size_t)i * ldm;
-                double acc = y[i];
+            const double* ri = Ms + i * ldm;
+            double acc = y[i];
 #pragma unroll
-                for (int c = 0; c < MLMAX; c++)
-                    if (c < i) acc = fma(-ri[c], y[c], acc);
-                y[i] = acc;
-            }
+            for (int c = 0; c < MLMAX; c++)
+                if (c < i) acc = fma(-ri[c], y[c], acc);
+            y[i] = acc;
         }
 #pragma unroll
         for (int i = MLMAX - 1; i >= 0; i--) {
-            if (i < ml) {
-                const double* ri = Ms + (size_t)i * ldm;
-                double acc = y[i];
+            const double* ri = Ms + i * ldm;
+            double acc = y[i];
 #pragma unroll
-                for (int c = 0; c < MLMAX; c++)
-                    if (c > i && c < ml) acc = fma(-ri[c], y[c], acc);
-                y[i] = acc / ri[i];
-            }
+            for (int c = 0; c < MLMAX; c++)
+                if (c > i) acc = fma(-ri[c], y[c], acc);
+            y[i] = acc / ri[i];
         }
 #pragma unroll
         for (int i = 0; i < MLMAX; i++)
@@ -164,26 +170,49 @@ __global__ void __launch_bounds__(PT, MLMAX > 40 ? 2 : 4) riccati_project_mech_k
     }
     __syncthreads();
 
-    // ---- Ã = A - Bλ X_A,  D = Bu - Bλ X_u: row i of body b sees the multipliers of the joints incident to b
-    for (int idx = tid; idx < n * W; idx += PT) {
-        const int i = idx / W, j = idx - W * i;
-        const int b = i / 12, kk = i - 12 * b;
-        double v = j < n ? A[(size_t)i * n + j] : Bu[(size_t)i * nu + (j - n)];
+    // ---- Ã = A - Bλ X_A,  D = Bu - Bλ X_u: one item = (body b, column j), the body's 12 rows in registers; they only see the multipliers of
+    // the joints incident to b (a solved multiplier row is read once per item, the Bλ block entries are broadcast loads)
+    for (int idx = tid; idx < Mv.nb * W; idx += PT) {
+        const int b = idx / W, j = idx - W * b;
+        const bool isA = j < n;
+        const double* src = isA ? A + (size_t)(12 * b) * n + j : Bu + (size_t)(12 * b) * nu + (j - n);
+        double* dst = isA ? At + (size_t)(12 * b) * n + j : D + (size_t)(12 * b) * nu + (j - n);
+        const int ld = isA ? n : nu;
+        double v[12];
+#pragma unroll
+        for (int kk = 0; kk < 12; kk++) v[kk] = src[(size_t)kk * ld];
         const int q1 = __ldg(Mv.bj_ptr + b + 1);
         for (int q = __ldg(Mv.bj_ptr + b); q < q1; q++) {
             const int jt = __ldg(Mv.bj_joint + q), side = __ldg(Mv.bj_side + q);
             const int r0 = __ldg(Mv.j_row0 + jt), dim = __ldg(Mv.j_dim + jt);
-            for (int rr = 0; rr < dim; rr++) v = fma(-Bc[(r0 + rr) * 24 + 12 * side + kk], Y[(size_t)(r0 + rr) * ldy + j], v);
+#pragma unroll
+            for (int rr = 0; rr < 6; rr++) {
+                if (rr < dim) {
+                    const double yr = Y[(size_t)(r0 + rr) * ldy + j];
+                    const double2* bc = reinterpret_cast<const double2*>(Bc + (r0 + rr) * 24 + 12 * side);
+#pragma unroll
+                    for (int k2 = 0; k2 < 6; k2++) {
+                        const double2 c2 = bc[k2];
+                        v[2 * k2] = fma(-c2.x, yr, v[2 * k2]);
+                        v[2 * k2 + 1] = fma(-c2.y, yr, v[2 * k2 + 1]);
+                    }
+                }
+            }
         }
-        if (j < n) At[(size_t)i * n + j] = v;
-        else D[(size_t)i * nu + (j - n)] = v;
+#pragma unroll
+        for (int kk = 0; kk < 12; kk++) dst[(size_t)kk * ld] = v[kk];
     }
 }
 
+int project_mlmax(int ml) { return ml <= 12 ? 12 : ml <= 24 ? 24 : ml <= 36 ? 36 : ml <= 48 ? 48 : 64; }
 size_t project_mech_smem(int n, int nu, int ml, int& ldm, int& ldy) {
-    ldm = ml | 1;
+    const int mlmax = project_mlmax(ml);
+    ldm = mlmax | 1;
     ldy = (n + nu) | 1;
-    return ((size_t)ml * ldm + (size_t)ml * ldy + (size_t)ml * 48) * sizeof(double) + (size_t)ml * 3 * sizeof(int);
+    // Ms [mlmax][ldm] | Y [ml][ldy] (+1 double so that Gc / Bc start 16-byte aligned) | Gc, Bc [ml][24] | rb, piv
+    size_t d = (size_t)mlmax * ldm + (size_t)ml * ldy;
+    d += d & 1;
+    return (d + (size_t)ml * 48) * sizeof(double) + (size_t)ml * 3 * sizeof(int);
 }
 
 }  // namespace
@@ -196,14 +225,18 @@ int riccati_project_mech_device(const DevMech& M, int P, int nu, const double* A
     int ldm, ldy;
     const size_t smem = project_mech_smem(n, nu, ml, ldm, ldy);
     if (smem > 100 * 1024) return 1;
-#define CCB_PROJ_LAUNCH(MLMAX_)                                                                                                          \
-    do {                                                                                                                                 \
-        CCB_CUDA(cudaFuncSetAttribute(riccati_project_mech_kernel<MLMAX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        riccati_project_mech_kernel<MLMAX_><<<P, PT, smem, stream>>>(M, n, nu, ml, ldm, ldy, A, Bu, Bl, G, At, D);                       \
+#define CCB_PROJ_LAUNCH(MLMAX_, MINB_)                                                                                                          \
+    do {                                                                                                                                        \
+        CCB_CUDA(cudaFuncSetAttribute(riccati_project_mech_kernel<MLMAX_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        riccati_project_mech_kernel<MLMAX_, MINB_><<<P, PT, smem, stream>>>(M, n, nu, ml, ldm, ldy, A, Bu, Bl, G, At, D);                       \
     } while (0)
-    if (ml <= 24) CCB_PROJ_LAUNCH(24);
-    else if (ml <= 40) CCB_PROJ_LAUNCH(40);
-    else CCB_PROJ_LAUNCH(64);
+    switch (project_mlmax(ml)) {
+        case 12: CCB_PROJ_LAUNCH(12, 6); break;
+        case 24: CCB_PROJ_LAUNCH(24, 5); break;
+        case 36: CCB_PROJ_LAUNCH(36, 4); break;
+        case 48: CCB_PROJ_LAUNCH(48, 3); break;
+        default: CCB_PROJ_LAUNCH(64, 2); break;
+    }
 #undef CCB_PROJ_LAUNCH
     g_launches++;
     CCB_CUDA(cudaGetLastError());
