@@ -592,7 +592,14 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cu
     const int G = 5 * M.nj, spw = 32 / G;
     const int grid = (a.B + spw - 1) / spw;
     const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
+    // Measured (r2, 4096 x 2000 cartpole bench, tools/ab_k1r.sh): the LQR-only instantiation is 4 % shorter in SASS and NOT faster --
+    // 32.0 ms against 31.4 ms for the one-for-all instantiation (31.6 ms with 160 registers): ptxas's register allocation at the 168 cap
+    // moves more than the removed PID / table code saves.  The split stays available for A/B runs (-DK1R_SPLIT).
+#ifdef K1R_SPLIT
     const bool gen = C.kind == CCB_CTRL_PID || C.kind == CCB_CTRL_TABLE;
+#else
+    const bool gen = true;
+#endif
 #define K1R_LAUNCH(NJ_)                                                                          \
     case NJ_:                                                                                    \
         if (gen) rollout_rows_kernel<NJ_, true><<<grid, 32, smem, stream>>>(M, C, a, ord);       \
