@@ -138,6 +138,10 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     for (int step = 0; step < A.steps; step++) {
         const int k = A.k0 + step;
         if (valid && A.storage) {   // saveToStorage!: (xc,qc,vc,wc) at the start of step k; the 5 lanes interleave the 13 words
+            // (Measured r2: staging the warp's contiguous 13 nb SPW doubles through the stash and streaming them out with consecutive lanes on
+            // consecutive doubles is SLOWER -- 34.7 ms against 32.9 ms with recording, and 32.6 against 31.4 ms without, because it shifts the
+            // register allocation at the 168 cap; the stores below already fill whole sectors, the five lanes of a joint cover 13 adjacent
+            // words, and at 1.7 GB per 33 ms the write stream is 0.8 % of the HBM roof.)
             double* out = A.storage + ((size_t)step * A.B + sys) * nst + 13 * b;
 #pragma unroll
             for (int i = 0; i < 13; i++)
