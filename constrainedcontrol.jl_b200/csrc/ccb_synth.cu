@@ -14,14 +14,14 @@ size_t riccati_sweep_ws_doubles(int n, int nu);
 int riccati_project_device(int P, int n, int nu, int ml, const double* A, const double* Bu, const double* Bl, const double* G, double* At, double* D,
                            double* ws, cudaStream_t stream);
 int riccati_project_mech_device(const DevMech& M, int P, int nu, const double* A, const double* Bu, const double* Bl, const double* G, double* At,
-                                double* D, cudaStream_t stream);
+                                double* D, double* ws, long long ws_stride, cudaStream_t stream);
 // projection of P linearisations of mechanism H: the structure-aware kernel (ccb_riccati_project.cu) when it applies, else the dense one
 static int project_linearisations(HostMech* H, int device, int P, int nu, const double* A, const double* Bu, const double* Bl, const double* G, double* At,
                                   double* D, double* ws, cudaStream_t stream) {
     const DevMech* view;
     int rc = get_dev_mech(H, device, &view);
     if (rc != CCB_OK) return rc;
-    rc = riccati_project_mech_device(*view, P, nu, A, Bu, Bl, G, At, D, stream);
+    rc = riccati_project_mech_device(*view, P, nu, A, Bu, Bl, G, At, D, ws, (long long)riccati_project_ws_doubles(12 * H->nb, nu, H->ml), stream);
     if (rc == 1) rc = riccati_project_device(P, 12 * H->nb, nu, H->ml, A, Bu, Bl, G, At, D, ws, stream);
     return rc;
 }

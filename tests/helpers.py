@@ -33,9 +33,21 @@ def oracle_lqr_gains(cc, orc, mech, cfg, horizon=None):
     return dict(K=K, N=N, zd=zd, Fd=Fd, eqc_idx=eqc_idx, om=om, lin=lin, res=res)
 
 
+def _log(kind, val):
+    """CCB_ERRLOG=<file>: every error a test evaluates is appended with its call site (tools: which bounds are tight, which are loose)"""
+    import os, sys
+    path = os.environ.get("CCB_ERRLOG")
+    if path:
+        f = sys._getframe(2)
+        with open(path, "a") as fh:
+            fh.write(f"{os.path.basename(f.f_code.co_filename)}:{f.f_lineno} {f.f_code.co_name} {kind} {val:.3e}\n")
+
+
 def rel_err(a, b):
     a = np.asarray(a); b = np.asarray(b)
-    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+    e = float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+    _log("rel", e)
+    return e
 
 
 def gain_err(a, b, floor=1e-3):
@@ -46,7 +58,9 @@ def gain_err(a, b, floor=1e-3):
     a = np.asarray(a, dtype=float); b = np.asarray(b, dtype=float)
     scale = np.maximum(np.abs(b), floor * np.abs(b).max(axis=-1, keepdims=True))
     scale = np.where(scale == 0.0, 1.0, scale)
-    return float((np.abs(a - b) / scale).max())
+    e = float((np.abs(a - b) / scale).max())
+    _log("elem", e)
+    return e
 
 
 def cartpole_states(cc, mech, B, seed=1, ymax=0.5, phimax=0.2):

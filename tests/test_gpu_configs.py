@@ -44,7 +44,9 @@ def test_c3_npendulum8_rollout_and_gains(cc, orc):
     Qd = cc.blockdiag(cfg["Q"]) * mech.dt; Rd = cc.blockdiag(cfg["R"]) * mech.dt
     # gains: the Riccati recursion of the upright 8-pendulum amplifies rounding (P ~ 1e7..1e11, gains ~1e6): literal CPU implementations
     # that differ only in summation order agree to ~2e-9 at N = 300, and any rounding-level asymmetry left in P is amplified to O(1)
-    # (the kernel keeps P exactly symmetric) -- so the bound here is 1e-7, not 1e-9
+    # (the kernel keeps P exactly symmetric) -- so the bound here is 1e-7, not 1e-9.  Evidence that this is the recursion and not
+    # the kernel: tests/test_oracle_quad.py / test_gpu_fullsize.py::test_npendulum_gains_against_binary128 (the literal Float64 recursion itself is
+    # 1.4e-7 element-relative away from the binary128 result at N = 300; measured GPU-vs-oracle here: 1.1e-8)
     out = cc.lqr_synthesize(mech, zd[None], np.zeros((1, 1)), eqc_idx, Qd, Rd, 300)
     lin = om.linearize(zd, [0.0], eqc_idx)
     ref = orc.dlqr(lin["A"], lin["Bu"], lin["Bl"], lin["G"], Qd, Rd, 300)
@@ -152,7 +154,7 @@ def test_c4_sawyer_tracking(cc, orc):
     tl = cc.TrackingLQR(mech, storage0, U.reshape(1, N, 7), cfg["eqcids"], cfg["Q"], cfg["R"])
     ref = om.tracking_dlqr(storage0.data[:, 0], U, eqc_idx, cc.blockdiag(cfg["Q"]) * mech.dt, cc.blockdiag(cfg["R"]) * mech.dt)
     assert tl.kexit[0] == ref["kexit"]
-    assert rel_err(tl.K[0], ref["Ku"]) < 1e-8
+    assert rel_err(tl.K[0], ref["Ku"]) < 1e-9
     mech.set_state_vector(st_init)
     B = 4
     st0 = sawyer_states(cc, mech, B, 4, 0.01)
@@ -160,20 +162,20 @@ def test_c4_sawyer_tracking(cc, orc):
     r = om.simulate(st0, N, ctrl=co, record=True, nthreads=4)
     out, fin, status = cc.simulate(mech, N * mech.dt, tl, record=True, states=st0, return_status=True)
     assert np.all(status > 0)
-    assert rel_err(out.data, r["storage"]) < 1e-8
+    assert rel_err(out.data, r["storage"]) < 1e-9
     # two reference trajectories, two perturbed starts each: 4 systems share 2 device-resident tables (ccb_ctrl_set_replication)
     U2 = np.stack([U, 0.5 * U])
     mech.set_state_vector(st_init)
     sto2, _, _ = cc.simulate(mech, N * mech.dt, cc.OpenLoop(mech, cfg["eqcids"], U2), record=True, states=mech.batch_states(2), return_status=True)
     tl2 = cc.TrackingLQR(mech, sto2, U2, cfg["eqcids"], cfg["Q"], cfg["R"]).replicate(2)
-    assert rel_err(tl2.K[0], ref["Ku"]) < 1e-8
+    assert rel_err(tl2.K[0], ref["Ku"]) < 1e-9
     out2, _, status2 = cc.simulate(mech, N * mech.dt, tl2, record=True, states=st0, return_status=True)
     assert np.all(status2 > 0)
     for s in range(4):
         t = s // 2
         co = om.make_ctrl(1, kind="tracking", eqc=eqc_idx, N=N, K=tl2.K[t], zd=sto2.data[:, t], Fd=U2[t])
         rr = om.simulate(st0[s:s + 1], N, ctrl=co, record=True)
-        assert rel_err(out2.data[:, s], rr["storage"][:, 0]) < 1e-8, s
+        assert rel_err(out2.data[:, s], rr["storage"][:, 0]) < 1e-9, s
 
 
 # ------------------------------------------------------------------------------------------------ C5: deltabot + PID sweep
@@ -197,7 +199,7 @@ def test_c5_deltabot_closed_chain(cc, orc):
     ol = cc.OpenLoop(mech, cfg["eqcids"], U)
     sto, fin, status = cc.simulate(mech, steps * mech.dt, ol, record=True, states=st0, return_status=True)
     assert np.all(status > 0) and np.all(r["iters"] > 0)
-    assert rel_err(sto.data, r["storage"]) < 1e-7        # rank-deficient KKT: both solves are noise-limited at ~reg level
+    assert rel_err(sto.data, r["storage"]) < 1e-9        # (measured 1e-13: the same regularisation in both implementations)
     assert np.abs(fin[0, 4, 0:3] - st0[0, 4, 0:3]).max() < 5e-3   # the feed-forward holds the platform (nearly) in place
 
 
@@ -224,7 +226,7 @@ def test_c5_deltabot_lqr_from_the_example_grid(cc, orc):
     o_ok = r["iters"] > 0
     assert np.array_equal(o_ok, ok[sel])
     both = o_ok & ok[sel]
-    assert rel_err(fin[sel][both], r["states"][both]) < 1e-6     # rank-deficient KKT + closed loop over 300 steps: noise-limited at ~reg level
+    assert rel_err(fin[sel][both], r["states"][both]) < 1e-9     # (measured 3e-13)
 
 
 def test_c5_pid_sweep_properties(cc, orc):
@@ -255,7 +257,7 @@ def test_c5_pid_sweep_properties(cc, orc):
     sto2, fin2, st2 = cc.simulate(mech, 10.0, pid2, record=True, states=st0[sub], return_status=True)
     good = st2 > 0
     assert np.array_equal(good, ok[sub])
-    assert rel_err(sto2.data[:, good], r["storage"][:, good]) < 1e-8
+    assert rel_err(sto2.data[:, good], r["storage"][:, good]) < 1e-9
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)
@@ -291,9 +293,13 @@ def test_c2_full_size_properties(cc, orc):
     assert rel_err(outs[1], outs[0]) < TOL and rel_err(outs[2], outs[0]) < TOL
     # oracle parity on a slice of the same batch at full length
     o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=20.0)
-    co = o["om"].make_ctrl(16, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
-    r = o["om"].simulate(st0[:16], steps, ctrl=co, nthreads=8)
-    assert rel_err(fin[:16], r["states"]) < TOL
+    # (every 8th system of the 4096 x 2000 bench batch: 512 systems, ~1 M sim steps of the CPU oracle on all host cores)
+    import os as _os
+    sel = np.arange(0, B, 8)
+    co = o["om"].make_ctrl(len(sel), kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
+    r = o["om"].simulate(st0[sel], steps, ctrl=co, nthreads=_os.cpu_count() or 8)
+    assert np.all(r["iters"] > 0)
+    assert rel_err(fin[sel], r["states"]) < TOL
 
 
 # ------------------------------------------------------------------------------------------------ branching URDF tree with fixed joints
@@ -327,7 +333,7 @@ def test_sawyer_simple_urdf_branching_tree_with_fixed_joints(cc, orc):
     r2 = om.simulate(st0, 60, ctrl=co, record=True, nthreads=6)
     sto2, fin2, status2 = cc.simulate(mech, 0.6, pid, record=True, states=st0, return_status=True)
     assert np.all(status2 > 0)
-    assert rel_err(sto2.data, r2["storage"]) < 1e-8
+    assert rel_err(sto2.data, r2["storage"]) < 1e-9
 
 
 def test_c4_sawyer_pid_and_infinite_horizon_lqr_on_the_long_chain_kernel(cc, orc):
@@ -348,9 +354,9 @@ def test_c4_sawyer_pid_and_infinite_horizon_lqr_on_the_long_chain_kernel(cc, orc
         pid = cc.PID(mech, ids, goals, P=P, I=I, D=D)
         sto, fin, status = cc.simulate(mech, 0.8, pid, record=True, states=st0, lanes=lanes, return_status=True)
         assert np.all(status > 0), lanes
-        assert rel_err(sto.data, r["storage"]) < 1e-8, lanes
+        assert rel_err(sto.data, r["storage"]) < 1e-9, lanes
         gi, gl = pid.pid_state(B)
-        assert rel_err(gi, integ) < 1e-8 and rel_err(gl, last) < 1e-8
+        assert rel_err(gi, integ) < 1e-9 and rel_err(gl, last) < 1e-9
     # horizon = Inf: Ntemp = ceil(10/dt) Riccati steps, only Ku[1] kept and applied at every k (lqr.jl:26,42,134)
     lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], math.inf, xd=cfg["xd"], qd=cfg["qd"])
     assert lqr.K.shape == (1, 1, 7, 84)
@@ -404,7 +410,7 @@ def test_sawyer_full_urdf(cc, orc):
     pid = cc.PID(mech, ids, goal, P=P, I=I, D=D)
     sto2, fin2, status2 = cc.simulate(mech, 0.6, pid, record=True, states=st0, return_status=True)
     assert np.all(status2 > 0) and np.all(r2["iters"] > 0)
-    assert rel_err(sto2.data, r2["storage"]) < 1e-8
+    assert rel_err(sto2.data, r2["storage"]) < 1e-9
     # linearsystem of the whole robot at the zero configuration (n = 168): block-sparse K2 vs the oracle's whole-residual AD
     zd = mech.state_vector()
     A, Bu, Bl, G = cc.linearsystem(mech, zd, np.zeros(len(eqc)), eqc)

@@ -183,11 +183,16 @@ def test_npendulum_gains_against_binary128(cc, links, N):
     e_gpu = gain_err(K, g["Ku_ref_rows"]); e_f64 = gain_err(g["Ku_f64_rows"], g["Ku_ref_rows"])
     print(f"n-pendulum {links} links, N {N}: GPU vs binary128 {e_gpu:.3e}, literal Float64 vs binary128 {e_f64:.3e}, max|P| {float(g['Pmax']):.2e}")
     if links == 8:
-        # both Float64 recursions random-walk at the amplified rounding level (measured ratios per row 0.2 .. 10, tools/r2_diag.py): the CUDA one
-        # stays within an order of magnitude of the literal one at every row and within 3x in the geometric mean over the rows
+        # Every Float64 realisation of this recursion random-walks at the amplified rounding level.  The fixture holds the band: the per-row
+        # maximum error (against binary128) of 16 runs of the LITERAL Float64 recursion whose inputs were perturbed by one ulp -- the recursion
+        # amplifies such a perturbation exactly as it amplifies its own rounding.  The CUDA recursion (another rounding sequence: projected form,
+        # DMMA tile order, reciprocal pivots) has to land inside 8x that band at every row (the band is the maximum of only 16 draws), and within 3x of its geometric mean over the rows.
         assert np.all(np.isfinite(K))
-        ratios = np.array([gain_err(K[i], g["Ku_ref_rows"][i]) / max(gain_err(g["Ku_f64_rows"][i], g["Ku_ref_rows"][i]), 1e-15) for i in range(len(g["rows"]))])
-        print("per-row ratio GPU / literal:", np.round(ratios, 2))
-        assert ratios.max() <= 16.0 and np.exp(np.log(np.maximum(ratios, 1e-3)).mean()) <= 3.0, ratios
+        band = np.maximum(g["f64_perturbed_rows"].max(axis=0), g["f64_vs_ref_elem_rows"])
+        e_rows = np.array([gain_err(K[i], g["Ku_ref_rows"][i]) for i in range(len(g["rows"]))])
+        print("per-row GPU error / band of the literal Float64 recursion under 1-ulp input perturbations:", np.round(e_rows / band, 2))
+        assert np.all(e_rows <= 8.0 * band), (e_rows, band)
+        gm = lambda v: float(np.exp(np.log(np.maximum(v, 1e-18)).mean()))
+        assert gm(e_rows) <= 3.0 * gm(band), (gm(e_rows), gm(band))
     else:
         assert e_f64 > 1e-3                                      # no Float64 implementation resolves this recursion: nothing to be parity-tested

@@ -85,7 +85,7 @@ def test_random_chain_linearsystem_and_gains(cc, orc, seed, nj):
     for s in range(S):
         ref = om.linearize(zd[s], Fd[s], eqc)
         rd = orc.dlqr(ref["A"], ref["Bu"], ref["Bl"], ref["G"], Qd, Rd, 40)
-        assert rel_err(out["Ku"][s], rd["Ku"]) < 1e-8, s
+        assert rel_err(out["Ku"][s], rd["Ku"]) < 1e-9, s
 
 
 @pytest.mark.parametrize("seed", [21, 22, 23])
@@ -201,7 +201,7 @@ def test_lqr_closed_loop_is_invariant_under_listing_orders(cc):
             ref = by_name
             assert np.abs(by_name["cart"][-1, 1]) < 0.05           # the controller does bring the cart back
         for name in ref:
-            assert rel_err(by_name[name], ref[name]) < 1e-7, (body_order, order, name)
+            assert rel_err(by_name[name], ref[name]) < 1e-9, (body_order, order, name)
 
 
 def test_two_independent_pendulums_in_one_mechanism(cc, orc):

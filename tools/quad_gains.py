@@ -37,7 +37,23 @@ ref = res[top]
 rows = sorted(set([0, (N - 1) // 4, (N - 1) // 2, 3 * (N - 1) // 4, N - 2]))
 errs = {p: dict(glob=float(np.abs(res[p]["Ku"] - ref["Ku"]).max() / max(1.0, np.abs(ref["Ku"]).max())),
                 elem=float(gain_err(res[p]["Ku"], ref["Ku"]))) for p in range(top)}
+# spread of the literal Float64 recursion under 1-ulp perturbations of its inputs: 16 realisations with every non-zero entry of A, Bu, Bλ, G
+# multiplied by (1 + u 2^-52), u in {-1, 0, 1}.  The recursion amplifies such a perturbation exactly as it amplifies its own rounding, so the
+# per-row maximum over the realisations is the band inside which ANY Float64 implementation of dlqr lands (tests/test_gpu_fullsize.py holds the
+# CUDA recursion to it).
+pert_rows = np.zeros((0, len(rows)))
+if links <= 8:
+    prng = np.random.default_rng(7)
+    def jitter(M):
+        return M * (1.0 + prng.integers(-1, 2, size=M.shape) * 2.0 ** -52)
+    errs_p = []
+    for t in range(16):
+        rp = orc.dlqr_mp(jitter(lin["A"]), jitter(lin["Bu"]), jitter(lin["Bl"]), jitter(lin["G"]), Q, R, N, prec=0)
+        errs_p.append([gain_err(rp["Ku"][r], ref["Ku"][r]) for r in rows])
+    pert_rows = np.array(errs_p)
+    print("1-ulp input perturbations, per-row max element-relative error of 16 Float64 realisations:", pert_rows.max(axis=0), flush=True)
 np.savez(os.path.join(ROOT, "tests", "golden", f"npend_quad_n{links}_N{N}.npz"), links=links, N=N, rows=np.array(rows), precision=top,
+         f64_perturbed_rows=pert_rows,
          Ku_ref_rows=ref["Ku"][rows], Ku_f64_rows=res[0]["Ku"][rows], iters_ref=ref["iters"], iters_f64=res[0]["iters"], Pmax=ref["Pmax"],
          f64_vs_ref_glob=errs[0]["glob"], f64_vs_ref_elem=errs[0]["elem"],
          f64_vs_ref_elem_rows=np.array([gain_err(res[0]["Ku"][r], ref["Ku"][r]) for r in rows]))
