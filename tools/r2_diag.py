@@ -44,7 +44,9 @@ if "tracking" in which:
     ro = om.simulate(st0, N, ctrl=om.make_ctrl(1, kind="table", eqc=eqc, U=U), record=True)
     tl = cc.TrackingLQR(mech, sto, U.reshape(1, N, 7), cfg["eqcids"], cfg["Q"], cfg["R"])
     ref = om.tracking_dlqr(sto.data[:, 0], U, eqc, cc.blockdiag(cfg["Q"]) * mech.dt, cc.blockdiag(cfg["R"]) * mech.dt)
+    x87 = om.tracking_dlqr(sto.data[:, 0], U, eqc, cc.blockdiag(cfg["Q"]) * mech.dt, cc.blockdiag(cfg["R"]) * mech.dt, prec=1)
     K = tl.K[0]
+    J(test="tracking_N2000_vs_x87", gpu_vs_x87=gain_err(K, x87["Ku"]), f64_vs_x87=gain_err(ref["Ku"], x87["Ku"]), kexit_x87=x87["kexit"])
     J(test="tracking_N2000", openloop_rel=rel_err(sto.data, ro["storage"]), iters_gpu=int(status[0]), iters_orc=int(ro["iters"][0]), kexit_gpu=int(tl.kexit[0]), kexit_orc=ref["kexit"],
       gain_err=gain_err(K, ref["Ku"]), rel=rel_err(K, ref["Ku"]), per_row=[gain_err(K[r], ref["Ku"][r]) for r in (0, 500, 1000, 1500, 1990, 1998)],
       Kmax=float(np.abs(ref["Ku"]).max()))
@@ -62,7 +64,7 @@ if "counts" in which:
         mech, cfg = cc.examples.sawyer(os.path.join(GOLD, "sawyer_arm.json"))
         rng = np.random.default_rng(3); st0 = np.zeros((24, mech.nb, 13))
         for s in range(24):
-            cc.urdf.zero_configuration(mech, {i: rng.uniform(-0.05, 0.05) for i in range(7)}); st0[s] = mech.state_vector()
+            cc.urdf.zero_configuration(mech, {i: rng.uniform(-0.01, 0.01) for i in range(7)}); st0[s] = mech.state_vector()
         cc.urdf.zero_configuration(mech)
         yield "C4_sawyer", mech, cfg, st0, 600, 20.0, (0, 1)
     for name, mech, cfg, st0, steps, horizon, lanes_list in cases():
