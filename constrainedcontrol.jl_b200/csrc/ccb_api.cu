@@ -87,7 +87,7 @@ int ccb_batch_create(ccb_mech* m, int32_t B, int32_t device, ccb_batch** out) {
 int ccb_batch_destroy(ccb_batch* b) {
     if (!b) return CCB_OK;
     cudaSetDevice(b->device);
-    cudaFree(b->state); cudaFree(b->lambda); cudaFree(b->status_dev); cudaFree(b->storage_dev);
+    cudaFree(b->state); cudaFree(b->lambda); cudaFree(b->status_dev); cudaFree(b->storage_dev); cudaFree(b->persist_buf);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     for (int i = 0; i < 2; i++) { if (b->ev_kernel[i]) cudaEventDestroy(b->ev_kernel[i]); if (b->ev_copy[i]) cudaEventDestroy(b->ev_copy[i]); }
@@ -271,6 +271,15 @@ static int simulate_launch(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t ste
     a.state = b->state; a.lambda = b->lambda; a.storage = storage_dev; a.status = status_dev;
     a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr; a.spw = opts ? opts->reserved : 0;
     a.status_accum = status_accum;
+    a.persist = nullptr; a.nchunks = 1; a.chunk_steps = steps;
+    if (steps >= 256 && view->rows_ok) {       // candidate for K1r's persistent time-sliced launch (the launcher decides)
+        const size_t need = (size_t)(b->B + 2) * sizeof(int);
+        if (b->persist_cap < need) {
+            cudaFree(b->persist_buf); b->persist_buf = nullptr; b->persist_cap = 0;
+            if (cudaMalloc(&b->persist_buf, need) == cudaSuccess) b->persist_cap = need; else cudaGetLastError();
+        }
+        a.persist = b->persist_buf;
+    }
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;
     a.line_iter = opts && opts->line_iter > 0 ? opts->line_iter : 10;

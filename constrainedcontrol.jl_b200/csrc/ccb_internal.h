@@ -138,13 +138,17 @@ struct SimArgs {
     double* s_out;      // [B][nb][6] solution (v2,w2) when knot_input
     int spw;            // chain kernel: systems per warp (0 = automatic)
     int status_accum;   // 1: this launch continues a rollout split over several launches: fold its counts into what `status` already holds
+    // persistent time-sliced launch of K1r (ccb_rollout_rows.cu): persist[0] = work counter, persist[1 + t] = chunks of triple t done (zeroed by
+    // the launcher); nullptr: plain launch
+    int* persist;
+    int nchunks, chunk_steps;
 };
 
 // status[s] = total Newton iterations of the rollout, negated if any step failed (0: failed before the first iteration); a continuing
 // launch (status_accum) adds to the earlier launches' count and keeps their failure flag
-__device__ __forceinline__ void write_status(const SimArgs& A, int sys, int total, bool failed) {
-    if (A.status_accum) {
-        const int o = A.status[sys];
+__device__ __forceinline__ void write_status(const SimArgs& A, int sys, int total, bool failed, bool later_chunk = false) {
+    if (A.status_accum || later_chunk) {
+        const int o = __ldcg(A.status + sys);
         if (o <= 0) failed = true;
         total += o < 0 ? -o : o;
     }
@@ -185,6 +189,7 @@ struct ccb_batch {
     double* storage_dev = nullptr; size_t storage_cap = 0;
     int* status_dev = nullptr;
     // record = true pipeline (ccb_simulate): device double buffer of trajectory chunks, drained by a copy stream while the next chunk computes
+    int* persist_buf = nullptr; size_t persist_cap = 0;      // work counter + per-triple chunk flags of K1r's persistent launches
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_kernel[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 };

@@ -245,7 +245,7 @@ int linearize_device(HostMech* H, int device, int S, double* d_zd, const double*
     std::memset(&C, 0, sizeof(C));
     C.kind = nu > 0 ? CCB_CTRL_TABLE : CCB_CTRL_NONE; C.nu = nu; C.N = 1; C.eqc = d_eqc; C.U = d_Fd; C.U_bs = nu;
     SimArgs a;
-    a.status_accum = 0;
+    a.status_accum = 0; a.persist = nullptr; a.nchunks = 1; a.chunk_steps = 1;
     a.state = d_zd; a.lambda = d_lam; a.storage = nullptr; a.status = d_status; a.B = S; a.k0 = 1; a.steps = 1;
     a.eps = opts && opts->eps > 0 ? opts->eps : 1e-10;
     a.newton_iter = opts && opts->newton_iter > 0 ? opts->newton_iter : 100;

@@ -55,8 +55,9 @@ __device__ __forceinline__ double rcp_fast(double x) {
 
 // GEN: false = the LQR-family instantiation (no controller, LQR Inf / finite, TrackingLQR): the PID and open-loop-table code (joint coordinate,
 // atan2, integrator state) is compiled out, which shortens the hot loop's SASS and frees registers; true = every law.
-template <int NJ, bool GEN>
-__global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
+// PERSIST: the time-sliced persistent variant (work loop below); a separate instantiation so that the plain kernel keeps its register allocation.
+template <int NJ, bool GEN, bool PERSIST>
+__global__ void __maxnreg__(PERSIST ? 248 : K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
     extern __shared__ __align__(16) double smem[];
     constexpr int G = 5 * NJ, SPW = 32 / G;
     double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
@@ -67,8 +68,6 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const int q = wl - sw * G;
     const int pos = q / 5, r = q - 5 * pos;         // joint position in the chain (0 = root), row in the joint
     const bool lane_ok = sw < SPW;
-    const int sys = blockIdx.x * SPW + sw;
-    const bool valid = lane_ok && sys < A.B;
     const int base = lane_ok ? sw * G : 0;           // first lane of my system (idle lanes shadow system slot 0, read only)
     const int g0 = base + 5 * pos;                   // first lane of my joint group
     const bool has_p = pos > 0, has_c = pos < NJ - 1;
@@ -78,7 +77,6 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const int cjt = has_c ? ord.joint[pos + 1] : -1;
     const int b = __ldg(M.j_child + jt);
     const int dim = __ldg(M.j_dim + jt), r0 = __ldg(M.j_row0 + jt);
-    const bool rowpad = !valid || r >= dim;          // padding row: identity in S, zero everywhere else
     const int rr = r < dim ? r : 0;
     const int kind = __ldg(M.row_kind + r0 + rr);
     const V3 pr = ldg3(M.row_proj + 3 * (r0 + rr));
@@ -110,12 +108,47 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     const double mass = cj[22], kdt = dt / mass;
     const double pkdt = has_p ? dt / cst[(pos - 1) * kCS + 22] : 0.0;
 
+    // ---- work loop.  Plain launch: ONE pass, the warp owns the systems blockIdx.x * SPW .. for all A.steps steps.
+    // Persistent launch (A.persist != 0, launch_rollout_rows): the grid is exactly two warps per SM sub-partition and the warps pull work items
+    // (chunk of steps, triple of systems) from a global counter in chunk-major order.  A batch whose warps do not divide evenly over the
+    // schedulers (4096 cartpoles = 1366 warps = 2.3 per scheduler) otherwise runs at the speed of the schedulers that got three warps while the
+    // others idle a third of the time; time-slicing the rollouts keeps every scheduler at two warps all the time.  An item may only start when the
+    // previous chunk of the same systems is stored (flag per triple, release / acquire through __threadfence); items are handed out in increasing
+    // order, so the chunk an item waits for is always in the hands of a running warp: no deadlock whatever the residency.
+    const int ntrip = (A.B + SPW - 1) / SPW;
+    for (int pass = 0;; pass++) {
+    int trip = blockIdx.x, chunk = 0;
+    if (PERSIST) {
+        int item = 0;
+        if (wl == 0) item = atomicAdd(A.persist, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= ntrip * A.nchunks) break;
+        chunk = item / ntrip;
+        trip = item - chunk * ntrip;
+        if (chunk > 0) {
+            if (wl == 0) {
+                const volatile int* flag = A.persist + 1 + trip;
+                while (*flag < chunk) __nanosleep(100);
+            }
+            __syncwarp();
+            __threadfence();
+        }
+    } else if (pass > 0) {
+        break;
+    }
+    const int step_lo = PERSIST ? chunk * A.chunk_steps : 0;
+    const int step_hi = PERSIST ? min(A.steps, step_lo + A.chunk_steps) : A.steps;
+    const int sys = trip * SPW + sw;
+    const bool valid = lane_ok && sys < A.B;
+    const bool rowpad = !valid || r >= dim;          // padding row: identity in S, zero everywhere else
+
     // ---- state in registers: the group's body (redundant in its 5 lanes) and my multiplier
     double z[13], lam;      // z[7..12]: (v1, w1) until the step's constants are formed, then the accepted Newton iterate (v2, w2)
     if (valid) {
+        // (__ldcg: in a persistent launch the previous chunk of these systems was written by another SM; L1 is not coherent)
 #pragma unroll
-        for (int i = 0; i < 13; i++) z[i] = A.state[(size_t)sys * nst + 13 * b + i];
-        lam = r < dim ? A.lambda[(size_t)sys * M.ml + r0 + r] : 0.0;
+        for (int i = 0; i < 13; i++) z[i] = PERSIST ? __ldcg(A.state + (size_t)sys * nst + 13 * b + i) : A.state[(size_t)sys * nst + 13 * b + i];
+        lam = r < dim ? (PERSIST ? __ldcg(A.lambda + (size_t)sys * M.ml + r0 + r) : A.lambda[(size_t)sys * M.ml + r0 + r]) : 0.0;
     } else {
 #pragma unroll
         for (int i = 0; i < 13; i++) z[i] = i == 3 ? 1.0 : 0.0;
@@ -135,7 +168,7 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
     int total_iters = 0;
     bool failed = false;
 
-    for (int step = 0; step < A.steps; step++) {
+    for (int step = step_lo; step < step_hi; step++) {
         const int k = A.k0 + step;
         if (valid && A.storage) {   // saveToStorage!: (xc,qc,vc,wc) at the start of step k; the 5 lanes interleave the 13 words
             // (Measured r2: staging the warp's contiguous 13 nb SPW doubles through the stash and streaming them out with consecutive lanes on
@@ -583,19 +616,43 @@ __global__ void __maxnreg__(K1R_MAXREG) rollout_rows_kernel(const DevMech M, con
             if (i % 5 == r) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     }
-    if (valid && A.status && q == 0) write_status(A, sys, total_iters, failed);
+    if (valid && A.status && q == 0) write_status(A, sys, total_iters, failed, PERSIST && chunk > 0);
+    if (PERSIST) {                                  // release: my stores, then the flag
+        __threadfence();
+        __syncwarp();
+        if (wl == 0) atomicExch(A.persist + 1 + trip, chunk + 1);
+    }
+    }   // work loop
 }
 
 }  // namespace
 
 // Eligibility (M.rows_ok, set in get_dev_mech): a single serial chain (every joint at a distinct depth) of at most 6 joints,
 // each of dimension <= 5.
-int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream) {
+int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a_in, cudaStream_t stream) {
     RowsOrder ord;
     for (int j = 0; j < 6; j++) ord.joint[j] = M.rows_order[j];
     const int G = 5 * M.nj, spw = 32 / G;
-    const int grid = (a.B + spw - 1) / spw;
-    const size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
+    int grid = (a_in.B + spw - 1) / spw;
+    size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
+    SimArgs a = a_in;
+    // Persistent time-sliced launch (see the work loop in the kernel): when the batch needs more one-warp CTAs than two per SM sub-partition but
+    // fewer than 1.3x that many, a plain launch runs at the three-warp time T(3) while persistent warps at two per scheduler need T(2) * W / slots
+    // (T(w) = 9.5 ms + 8 ms w for 2000 cartpole steps: break-even at W = 1.3 slots).  Not for laws with controller state on the device (PID).
+    static int nsm = 0;
+    if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    const int slots2 = 8 * nsm;
+    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && grid > slots2 && (long long)grid * 10 < (long long)slots2 * 13 &&
+                         C.kind != CCB_CTRL_PID && !getenv("CCB_K1R_NO_PERSIST");
+    if (persist) {
+        a.chunk_steps = (a.steps + 15) / 16;
+        a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps;
+        CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(1 + grid) * sizeof(int), stream));
+        grid = slots2;
+        smem = std::max(smem, (size_t)26 * 1024);        // at most 8 CTAs (= 2 warps per scheduler) per SM
+    } else {
+        a.persist = nullptr; a.nchunks = 1; a.chunk_steps = a.steps;
+    }
     // Measured (r2, 4096 x 2000 cartpole bench, tools/ab_k1r.sh): the LQR-only instantiation is 4 % shorter in SASS and NOT faster --
     // 32.0 ms against 31.4 ms for the one-for-all instantiation (31.6 ms with 160 registers): ptxas's register allocation at the 168 cap
     // moves more than the removed PID / table code saves.  The split stays available for A/B runs (-DK1R_SPLIT).
@@ -604,16 +661,18 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a, cu
 #else
     const bool gen = true;
 #endif
-#define K1R_LAUNCH(NJ_)                                                                          \
-    case NJ_:                                                                                    \
-        if (gen) rollout_rows_kernel<NJ_, true><<<grid, 32, smem, stream>>>(M, C, a, ord);       \
-        else rollout_rows_kernel<NJ_, false><<<grid, 32, smem, stream>>>(M, C, a, ord);          \
+#define K1R_LAUNCH(NJ_)                                                                                   \
+    case NJ_:                                                                                             \
+        if (persist) rollout_rows_kernel<NJ_, true, true><<<grid, 32, smem, stream>>>(M, C, a, ord);      \
+        else if (gen) rollout_rows_kernel<NJ_, true, false><<<grid, 32, smem, stream>>>(M, C, a, ord);    \
+        else rollout_rows_kernel<NJ_, false, false><<<grid, 32, smem, stream>>>(M, C, a, ord);            \
         break;
     switch (M.nj) {
         K1R_LAUNCH(1) K1R_LAUNCH(2) K1R_LAUNCH(3) K1R_LAUNCH(4) K1R_LAUNCH(5)
         default:
-            if (gen) rollout_rows_kernel<6, true><<<grid, 32, smem, stream>>>(M, C, a, ord);
-            else rollout_rows_kernel<6, false><<<grid, 32, smem, stream>>>(M, C, a, ord);
+            if (persist) rollout_rows_kernel<6, true, true><<<grid, 32, smem, stream>>>(M, C, a, ord);
+            else if (gen) rollout_rows_kernel<6, true, false><<<grid, 32, smem, stream>>>(M, C, a, ord);
+            else rollout_rows_kernel<6, false, false><<<grid, 32, smem, stream>>>(M, C, a, ord);
             break;
     }
 #undef K1R_LAUNCH

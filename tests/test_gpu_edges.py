@@ -152,3 +152,33 @@ def test_record_pipeline_is_bit_identical_to_one_launch(cc, monkeypatch):
         assert np.array_equal(x, y)
     assert np.array_equal(a[6][0], b[6][0]) and np.array_equal(a[6][1], b[6][1])
     assert np.all(a[2] > 0) and np.all(a[5] != 0)
+
+
+def test_persistent_time_sliced_launch_is_bit_identical(cc, monkeypatch):
+    """K1r's persistent launch (a batch of 1184 < W < 1.3 x 1184 warps: two warps per SM sub-partition pull (chunk of steps, triple of systems)
+    work items) must give the bits of the plain launch: states, multipliers and accumulated Newton counts, for LQR (finite horizon ending
+    inside the rollout), open-loop tables and the uncontrolled mechanism.  B = 3700 cartpoles -> 1234 warps."""
+    mech, cfg = cc.examples.cartpole()
+    B, steps = 3700, 272                                         # chunks of 17 steps, the last one ragged
+    st0 = cartpole_states(cc, mech, B, seed=11)
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], 2.0, xd=cfg["xd"])       # N = 200 < steps
+    U = 0.3 * np.sin(np.arange(steps)[:, None] * 0.05)
+    out = {}
+    for mode in ("plain", "persistent"):
+        if mode == "plain":
+            monkeypatch.setenv("CCB_K1R_NO_PERSIST", "1")
+        else:
+            monkeypatch.delenv("CCB_K1R_NO_PERSIST")
+        res = []
+        for ctrl in (lqr, cc.OpenLoop(mech, cfg["eqcids"], U), None):
+            batch = cc.Batch(mech, B)
+            batch.set_state(st0)
+            n0 = cc._lib.lib().ccb_launch_count()
+            _, status = batch.simulate(ctrl, 1, steps)
+            fin, lam = batch.get_state(want_lambda=True)
+            res.append((fin, lam, status))
+        out[mode] = res
+    for a, b in zip(out["plain"], out["persistent"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.all(a[2] > 0)
