@@ -19,6 +19,8 @@
 // Same algorithm and semantics as K1 / K1c: simulate! loop of ConstrainedDynamics.jl with the
 // control laws of reference src/control/lqr.jl:89-139, lqr_tracking.jl:46-71, pid.jl:43-88 fused.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "ccb_dev_math.cuh"
 #include "ccb_internal.h"
 
@@ -36,6 +38,10 @@ struct RowsOrder { int joint[6]; };
 // (measured on the 4096x2000 cartpole batch: 128 -> 42.5 ms, 144 -> 40.3, 168 -> 37.9, 184 -> 48.7, 200 -> 48.1, 255 -> 43.3)
 #ifndef K1R_MAXREG
 #define K1R_MAXREG 168
+#endif
+// the persistent variant runs exactly two warps per scheduler: up to 248 registers fit (8 x 32 x 248 <= 64 K)
+#ifndef K1R_PERSIST_MAXREG
+#define K1R_PERSIST_MAXREG 248
 #endif
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -57,7 +63,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
 // atan2, integrator state) is compiled out, which shortens the hot loop's SASS and frees registers; true = every law.
 // PERSIST: the time-sliced persistent variant (work loop below); a separate instantiation so that the plain kernel keeps its register allocation.
 template <int NJ, bool GEN, bool PERSIST>
-__global__ void __maxnreg__(PERSIST ? 248 : K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
+__global__ void __maxnreg__(PERSIST ? K1R_PERSIST_MAXREG : K1R_MAXREG) rollout_rows_kernel(const DevMech M, const DevCtrl C, const SimArgs A, const RowsOrder ord) {
     extern __shared__ __align__(16) double smem[];
     constexpr int G = 5 * NJ, SPW = 32 / G;
     double* gk = smem;                      // [SPW][NJ][kGS]: row t of a joint at t*12: GkA[6] | GkB[6]
@@ -109,31 +115,38 @@ __global__ void __maxnreg__(PERSIST ? 248 : K1R_MAXREG) rollout_rows_kernel(cons
     const double pkdt = has_p ? dt / cst[(pos - 1) * kCS + 22] : 0.0;
 
     // ---- work loop.  Plain launch: ONE pass, the warp owns the systems blockIdx.x * SPW .. for all A.steps steps.
-    // Persistent launch (A.persist != 0, launch_rollout_rows): the grid is exactly two warps per SM sub-partition and the warps pull work items
-    // (chunk of steps, triple of systems) from a global counter in chunk-major order.  A batch whose warps do not divide evenly over the
-    // schedulers (4096 cartpoles = 1366 warps = 2.3 per scheduler) otherwise runs at the speed of the schedulers that got three warps while the
-    // others idle a third of the time; time-slicing the rollouts keeps every scheduler at two warps all the time.  An item may only start when the
-    // previous chunk of the same systems is stored (flag per triple, release / acquire through __threadfence); items are handed out in increasing
-    // order, so the chunk an item waits for is always in the hands of a running warp: no deadlock whatever the residency.
+    // Persistent launch (PERSIST, launch_rollout_rows): the grid is exactly two warps per SM sub-partition (W workers) for a batch of
+    // ntrip = W + extra warp-loads ("triples" of systems), 0 < extra < 0.3 W.  A plain launch of such a batch runs at the speed of the schedulers
+    // that got three warps while the others idle a third of the time (4096 cartpoles = 1366 warps = 2.3 per scheduler).  Here the rollout is cut
+    // into nchunks chunks of steps and the schedule is STATIC: worker w simulates its own triple w chunk after chunk (no dependency on anybody)
+    // and, after its chunk c, one chunk of an EXTRA triple when its turn comes -- extra triple W + j, chunk c goes to worker (c extra + j) mod W,
+    // so the extra work rotates over the workers (everybody ends up with nchunks + nchunks extra / W +- 1 items) and the chunk an extra item
+    // continues was finished one whole round earlier by another worker: the flag it checks (release / acquire through __threadfence) is
+    // practically always set.  (A first version handed (chunk, triple) items out from a global counter: workers picked up chunks whose
+    // predecessor was still running elsewhere and spun, the spinning warps stole issue slots from their scheduler mates, the convoy collapsed
+    // to 170 ms instead of 31 ms -- tools/persist_probe.py.)
     const int ntrip = (A.B + SPW - 1) / SPW;
-    for (int pass = 0;; pass++) {
+    const int nworkers = gridDim.x, extra = PERSIST ? ntrip - nworkers : 0;
+    for (int slot = 0;; slot++) {
     int trip = blockIdx.x, chunk = 0;
     if (PERSIST) {
-        int item = 0;
-        if (wl == 0) item = atomicAdd(A.persist, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= ntrip * A.nchunks) break;
-        chunk = item / ntrip;
-        trip = item - chunk * ntrip;
-        if (chunk > 0) {
-            if (wl == 0) {
-                const volatile int* flag = A.persist + 1 + trip;
-                while (*flag < chunk) __nanosleep(100);
+        chunk = slot >> 1;
+        if (chunk >= A.nchunks) break;
+        if (slot & 1) {
+            int j = ((int)blockIdx.x - chunk * extra) % nworkers;
+            if (j < 0) j += nworkers;
+            if (j >= extra) continue;
+            trip = nworkers + j;
+            if (chunk > 0) {
+                if (wl == 0) {
+                    const volatile int* flag = A.persist + 1 + trip;
+                    while (*flag < chunk) __nanosleep(2000);
+                }
+                __syncwarp();
+                __threadfence();
             }
-            __syncwarp();
-            __threadfence();
         }
-    } else if (pass > 0) {
+    } else if (slot > 0) {
         break;
     }
     const int step_lo = PERSIST ? chunk * A.chunk_steps : 0;
@@ -617,10 +630,10 @@ __global__ void __maxnreg__(PERSIST ? 248 : K1R_MAXREG) rollout_rows_kernel(cons
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     }
     if (valid && A.status && q == 0) write_status(A, sys, total_iters, failed, PERSIST && chunk > 0);
-    if (PERSIST) {                                  // release: my stores, then the flag
-        __threadfence();
-        __syncwarp();
-        if (wl == 0) atomicExch(A.persist + 1 + trip, chunk + 1);
+    if (PERSIST) {
+        if (trip >= nworkers) __threadfence();      // an extra triple moves on to another worker: release my stores, then the flag
+        __syncwarp();                               // (own triple: the next chunk reloads what the other lanes of this warp stored)
+        if (trip >= nworkers && wl == 0) atomicExch(A.persist + 1 + trip, chunk + 1);
     }
     }   // work loop
 }
@@ -637,19 +650,27 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a_in,
     size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
     SimArgs a = a_in;
     // Persistent time-sliced launch (see the work loop in the kernel): when the batch needs more one-warp CTAs than two per SM sub-partition but
-    // fewer than 1.3x that many, a plain launch runs at the three-warp time T(3) while persistent warps at two per scheduler need T(2) * W / slots
-    // (T(w) = 9.5 ms + 8 ms w for 2000 cartpole steps: break-even at W = 1.3 slots).  Not for laws with controller state on the device (PID).
+    // fewer than 1.2x that many, a plain launch runs at the three-warp time T(3) while persistent warps at two per scheduler need about
+    // T(2) * W / slots.  Measured on 2000 cartpole steps (tools/persist_probe.py): 4096 systems (W = 1.15 slots) 29.7 ms against 31.7 ms plain;
+    // 4400 systems (1.24 slots) 31.8 against 32.1 ms: break-even.  Not for laws with controller state on the device (PID).
     static int nsm = 0;
     if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
     const int slots2 = 8 * nsm;
-    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && grid > slots2 && (long long)grid * 10 < (long long)slots2 * 13 &&
+    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && ((grid > slots2 && (long long)grid * 10 <= (long long)slots2 * 12) || getenv("CCB_K1R_FORCE_PERSIST")) &&
                          C.kind != CCB_CTRL_PID && !getenv("CCB_K1R_NO_PERSIST");
     if (persist) {
-        a.chunk_steps = (a.steps + 15) / 16;
+        const int want = std::max(1, std::min(32, a.steps / 32));          // 32 chunks of >= 32 steps: every worker gets 32 + 32 extra / slots +- 1 items
+        a.chunk_steps = (a.steps + want - 1) / want;
         a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps;
-        CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(1 + grid) * sizeof(int), stream));
-        grid = slots2;
-        smem = std::max(smem, (size_t)26 * 1024);        // at most 8 CTAs (= 2 warps per scheduler) per SM
+        CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(a.B + 2) * sizeof(int), stream));      // the whole buffer (ccb_api.cu: B + 2 ints)
+        grid = slots2;        // compiled for 248 registers, at most 8 one-warp CTAs (= 2 warps per scheduler) fit an SM; with fewer registers
+        if (K1R_PERSIST_MAXREG < 224) smem = std::max(smem, (size_t)26 * 1024);     // shared memory caps the residency at 8 instead
+        if (const char* e = getenv("CCB_K1R_CHUNKS")) { const int nc = std::max(1, atoi(e)); a.chunk_steps = (a.steps + nc - 1) / nc; a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps; }
+        if (getenv("CCB_K1R_DEBUG")) {
+            int occ = -1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_rows_kernel<2, true, true>, 32, smem);
+            fprintf(stderr, "K1r persistent: grid %d, nchunks %d x %d steps, smem %zu, occupancy(NJ=2) %d CTAs/SM\n", grid, a.nchunks, a.chunk_steps, smem, occ);
+        }
     } else {
         a.persist = nullptr; a.nchunks = 1; a.chunk_steps = a.steps;
     }
