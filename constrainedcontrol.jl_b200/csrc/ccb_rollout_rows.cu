@@ -655,9 +655,11 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a_in,
     // 4400 systems (1.24 slots) 31.8 against 32.1 ms: break-even.  Not for laws with controller state on the device (PID).
     static int nsm = 0;
     if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    const int slots2 = 8 * nsm;
-    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && ((grid > slots2 && (long long)grid * 10 <= (long long)slots2 * 12) || getenv("CCB_K1R_FORCE_PERSIST")) &&
-                         C.kind != CCB_CTRL_PID && !getenv("CCB_K1R_NO_PERSIST");
+    // (the same with ONE warp per scheduler -- 2048 systems = 683 warps on 592 schedulers, the 2-GPU share of the bench batch -- does not pay:
+    // 24.4 ms against 24.1 ms plain; nothing pins four one-warp CTAs of an SM to four different schedulers)
+    int slots2 = 8 * nsm;
+    if (!(grid > slots2 && (long long)grid * 10 <= (long long)slots2 * 12) && !getenv("CCB_K1R_FORCE_PERSIST")) slots2 = 0;
+    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && slots2 > 0 && C.kind != CCB_CTRL_PID && !getenv("CCB_K1R_NO_PERSIST");
     if (persist) {
         const int want = std::max(1, std::min(32, a.steps / 32));          // 32 chunks of >= 32 steps: every worker gets 32 + 32 extra / slots +- 1 items
         a.chunk_steps = (a.steps + want - 1) / want;
