@@ -600,7 +600,7 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "sim_steps": SIM_STEPS, "mechanism": "cartpole (2 bodies, 2 joints, m_lambda=10)",
                        "newton_eps": 1e-10, "gains": gain_src, "l2": "flushed (256 MB write) between timed iterations",
                        "parallelism": f"dp{world} (independent systems, no collective on the step path)",
-                       "kernel": "rollout_rows_kernel<2> (K1r: one lane per constraint row)" if args.lanes in (0, 5) else f"lanes={args.lanes}"},
+                       "kernel": "rollout_rows_kernel<2> (K1r: one lane per constraint row; persistent time-sliced launch, 2 warps per SM sub-partition)" if args.lanes in (0, 5) else f"lanes={args.lanes}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = 2*8*(13*Nb+m_lambda) per system-step (SURVEY 8(d)); the fused kernel keeps state on chip, "
