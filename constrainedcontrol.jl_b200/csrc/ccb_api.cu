@@ -272,7 +272,7 @@ static int simulate_launch(ccb_batch* b, ccb_ctrl* ctrl, int32_t k0, int32_t ste
     a.B = b->B; a.k0 = k0; a.steps = steps; a.knot_input = 0; a.s_out = nullptr; a.spw = opts ? opts->reserved : 0;
     a.status_accum = status_accum;
     a.persist = nullptr; a.nchunks = 1; a.chunk_steps = steps;
-    if (steps >= 256 && view->rows_ok) {       // candidate for K1r's persistent time-sliced launch (the launcher decides)
+    if (steps >= 256) {       // candidate for the persistent time-sliced launches of K1r / K1m (the launchers decide)
         const size_t need = (size_t)(b->B + 2) * sizeof(int);
         if (b->persist_cap < need) {
             cudaFree(b->persist_buf); b->persist_buf = nullptr; b->persist_cap = 0;

@@ -59,7 +59,6 @@ __global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCt
     int* jorder = reinterpret_cast<int*>(ured2 + 8 * nj);   // [nj] joint at chain position
 
     const int q = threadIdx.x;
-    const int sys = blockIdx.x;
     const bool lane_ok = q < 5 * nj;
     const int pos = lane_ok ? q / 5 : 0, r = lane_ok ? q - 5 * pos : q % 5;
     const bool has_p = pos > 0, has_c = pos < nj - 1;
@@ -101,10 +100,50 @@ __global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCt
     const double pkdt = has_p ? dt / cst[(pos - 1) * kCS + 22] : 0.0;
     const int ppos = has_p ? pos - 1 : pos;
 
+    // ---- work loop.  Plain launch (A.persist == nullptr): one pass, the CTA owns system blockIdx.x for all A.steps steps.
+    // Persistent time-sliced launch (launch_rollout_mw): W = gridDim.x resident CTAs for B = q W + e systems.  The rollouts are cut into
+    // A.nchunks chunks of steps with a STATIC schedule: in round c worker w simulates chunk c of its own systems w, w + W, .. (nobody else ever
+    // touches them) and then, when its turn comes, chunk c of one of the e extra systems -- extra system q W + j goes to worker (c e + j) mod W, so
+    // the extra work rotates over the workers and the chunk an extra item continues was stored a whole round earlier by another CTA (flag per
+    // system, release / acquire through __threadfence; state reloaded with ld.cg since L1 is not coherent).  This lets a batch that does not fit
+    // one wave of the spill-free 255-register variant run on it anyway: 1024 Sawyer arms on 592 CTAs.  Bit-identical to the plain launch.
+    const bool persist = A.persist != nullptr;
+    const int nworkers = gridDim.x, qown = persist ? A.B / nworkers : 1, extra = persist ? A.B - qown * nworkers : 0;
     double z[13], s[6], lam;
+    for (int slot = 0;; slot++) {
+    int sys = blockIdx.x, chunk = 0;
+    if (persist) {
+        chunk = slot / (qown + 1);
+        if (chunk >= A.nchunks) break;
+        const int i = slot - chunk * (qown + 1);
+        if (i < qown) {
+            sys = (int)blockIdx.x + i * nworkers;
+        } else {
+            int j = ((int)blockIdx.x - (int)(((long long)chunk * extra) % nworkers)) % nworkers;
+            if (j < 0) j += nworkers;
+            if (j >= extra) continue;                 // CTA-uniform
+            sys = qown * nworkers + j;
+            if (chunk > 0) {
+                if (q == 0) {
+                    const volatile int* flag = A.persist + 1 + sys;
+                    while (*flag < chunk) __nanosleep(2000);
+                }
+                __syncthreads();
+                __threadfence();
+            }
+        }
+    } else if (slot > 0) {
+        break;
+    }
+    const int step_lo = persist ? chunk * A.chunk_steps : 0;
+    const int step_hi = persist ? min(A.steps, step_lo + A.chunk_steps) : A.steps;
+    if (persist) {
+        for (int i = q; i < 5 * nj + 5; i += blockDim.x) xl[i] = 0.0;
+        __syncthreads();
+    }
 #pragma unroll
-    for (int i = 0; i < 13; i++) z[i] = A.state[(size_t)sys * nst + 13 * b + i];
-    lam = (lane_ok && r < dim) ? A.lambda[(size_t)sys * M.ml + r0 + r] : 0.0;
+    for (int i = 0; i < 13; i++) z[i] = persist ? __ldcg(A.state + (size_t)sys * nst + 13 * b + i) : A.state[(size_t)sys * nst + 13 * b + i];
+    lam = (lane_ok && r < dim) ? (persist ? __ldcg(A.lambda + (size_t)sys * M.ml + r0 + r) : A.lambda[(size_t)sys * M.ml + r0 + r]) : 0.0;
 #pragma unroll
     for (int i = 0; i < 6; i++) s[i] = 0.0;
 
@@ -122,7 +161,7 @@ __global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCt
     int total_iters = 0;
     bool failed = false;
 
-    for (int step = 0; step < A.steps; step++) {
+    for (int step = step_lo; step < step_hi; step++) {
         const int k = A.k0 + step;
         if (lane_ok && A.storage) {
             double* out = A.storage + ((size_t)step * A.B + sys) * nst + 13 * b;
@@ -619,7 +658,14 @@ __global__ void __maxnreg__(MAXR) rollout_mw_kernel(const DevMech M, const DevCt
             if (i % 5 == r) A.state[(size_t)sys * nst + 13 * b + i] = z[i];
         if (r < dim) A.lambda[(size_t)sys * M.ml + r0 + r] = lam;
     }
-    if (A.status && q == 0) write_status(A, sys, total_iters, failed);
+    if (A.status && q == 0) write_status(A, sys, total_iters, failed, persist && chunk > 0);
+    if (persist) {
+        const bool shared = sys >= qown * nworkers;      // an extra system moves on to another CTA: release my stores, then the flag
+        if (shared) __threadfence();
+        __syncthreads();                                  // (own systems: the next chunk reloads what the other threads of this CTA stored)
+        if (shared && q == 0) atomicExch(A.persist + 1 + sys, chunk + 1);
+    }
+    }   // work loop
 }
 
 }  // namespace
@@ -629,7 +675,8 @@ bool mw_kernel_eligible(const DevMech& M) {
     return M.is_chain && M.nj >= 1 && M.chain_max_dim <= 5 && M.chain_max_depth == M.nj - 1 && 5 * M.nj <= 1024;
 }
 
-int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cudaStream_t stream) {
+int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a_in, cudaStream_t stream) {
+    SimArgs a = a_in;
     const int nj = M.nj;
     const int threads = ((5 * nj + 31) / 32) * 32;
     const size_t doubles = (size_t)nj * kGS + (size_t)nj * kCS + (size_t)nj * 8 + (size_t)nj * 6 + (size_t)nj * 9 + (5 * nj + 5) + (size_t)nj * 6 + 48 +
@@ -652,9 +699,9 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
     } while (0)
 #define CCB_MW_LAUNCH(NJT)                                                                                                            \
     do {                                                                                                                             \
-        if (pick == 0) rollout_mw_kernel<NJT, 255><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                          \
-        else if (pick == 1) rollout_mw_kernel<NJT, 168><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                     \
-        else rollout_mw_kernel<NJT, 128><<<a.B, threads, smem, stream>>>(M, C, a, M.chain_depth);                                    \
+        if (pick == 0) rollout_mw_kernel<NJT, 255><<<grid, threads, smem, stream>>>(M, C, a, M.chain_depth);                         \
+        else if (pick == 1) rollout_mw_kernel<NJT, 168><<<grid, threads, smem, stream>>>(M, C, a, M.chain_depth);                    \
+        else rollout_mw_kernel<NJT, 128><<<grid, threads, smem, stream>>>(M, C, a, M.chain_depth);                                   \
     } while (0)
     // the attribute / occupancy queries are per (device, chain length, shared-memory size): remembered between launches
     // (the shared-memory opt-in is raised to the device maximum once per variant, so a remembered entry never needs it again)
@@ -692,6 +739,24 @@ int launch_rollout_mw(const DevMech& M, const DevCtrl& C, const SimArgs& a, cuda
     if (const char* e = getenv("CCB_K1M_REGS")) {      // experiments: force a variant
         const int v = atoi(e);
         for (int i = 0; i < 3; i++) if (caps[i] == v) pick = i;
+    }
+    // Persistent time-sliced launch (work loop in the kernel): a batch that does not fit one wave of the spill-free 255-register variant runs on
+    // exactly that wave anyway, W = sms * occ[0] CTAs simulating B systems in chunks of steps.  Measured on 2000 Sawyer steps
+    // (tools/k1m_probe.py): the 255-register variant carries 592 systems in 38.0 ms (15.6 systems/ms), the 128-register variant that a plain
+    // launch needs to get 1024 systems into one wave 1024 in 73.4 ms (13.9/ms, spills), 168 registers 592 in 48.8 ms.  Two-warp CTAs only
+    // (Sawyer arm, 8-pendulum): longer chains want more resident warps than 255 registers allow.  Not for PID (controller state on the device).
+    int grid = a.B;
+    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && wpc <= 2 && occ[0] > 0 && (long long)a.B > (long long)sms * occ[0] &&
+                         C.kind != CCB_CTRL_PID && !getenv("CCB_K1M_NO_PERSIST") && !getenv("CCB_K1M_REGS");
+    if (persist) {
+        pick = 0;
+        grid = sms * occ[0];
+        const int want = std::max(1, std::min(32, a.steps / 32));
+        a.chunk_steps = (a.steps + want - 1) / want;
+        a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps;
+        CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(a.B + 2) * sizeof(int), stream));
+    } else {
+        a.persist = nullptr; a.nchunks = 1; a.chunk_steps = a.steps;
     }
     switch (nj) {
         case 7: CCB_MW_LAUNCH(7); break;

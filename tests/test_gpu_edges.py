@@ -182,3 +182,39 @@ def test_persistent_time_sliced_launch_is_bit_identical(cc, monkeypatch):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
         assert np.all(a[2] > 0)
+
+
+@pytest.mark.parametrize("B", [700, 1300])
+def test_persistent_launch_of_the_long_chain_kernel_is_bit_identical(cc, monkeypatch, B):
+    """K1m's persistent time-sliced launch (a batch beyond one wave of the 255-register variant: 592 CTAs simulate B Sawyer arms in chunks of
+    steps; B = 700: one own system per CTA + 108 rotating extras, B = 1300: two own systems + 116 extras) gives the bits of the plain launch."""
+    import os
+    mech, cfg = cc.examples.sawyer(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sawyer_arm.json"))
+    steps = 272
+    rng = np.random.default_rng(17)
+    st0 = np.zeros((B, mech.nb, 13))
+    for s in range(B):
+        cc.urdf.zero_configuration(mech, {i: rng.uniform(-0.01, 0.01) for i in range(7)})
+        st0[s] = mech.state_vector()
+    cc.urdf.zero_configuration(mech)
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], 2.0, xd=cfg["xd"], qd=cfg["qd"])     # N = 200 < steps
+    out = {}
+    for mode in ("plain", "persistent"):
+        if mode == "plain":                                   # the same 255-register variant, launched plainly (two or three waves)
+            monkeypatch.setenv("CCB_K1M_NO_PERSIST", "1")
+            monkeypatch.setenv("CCB_K1M_REGS", "255")          # (the register variants differ from each other at the 1e-14 level: ptxas fuses
+        else:                                                  # multiplies and adds differently under different caps)
+            monkeypatch.delenv("CCB_K1M_NO_PERSIST")
+            monkeypatch.delenv("CCB_K1M_REGS")
+        res = []
+        for ctrl in (lqr, None):
+            batch = cc.Batch(mech, B)
+            batch.set_state(st0)
+            _, status = batch.simulate(ctrl, 1, steps)
+            fin, lam = batch.get_state(want_lambda=True)
+            res.append((fin, lam, status))
+        out[mode] = res
+    for a, b in zip(out["plain"], out["persistent"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.all(a[2] > 0)
