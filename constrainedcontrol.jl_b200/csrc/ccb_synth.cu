@@ -262,9 +262,12 @@ int ccb_synth_phase_ms(double out[4]) {
 
 // LQR synthesis on the device: linearsystem (K1 knot solve + K2) -> projection -> Riccati sweep (K3/K4).  The gain table
 // d_Ku [S][N-1][nu][n] is allocated here and handed to the caller (cudaFree).
+// pipe_n > 0 (ccb_lqr_synthesize_peers, shards of more than one wave of sweep CTAs): the sweep runs in groups of one wave and the finished
+// tables of a group are copied to the pipe_n tables (own + peers, slot pipe_off + s) by the copy engines on a second stream WHILE the next
+// group sweeps.
 static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, const double* Fd, const int32_t* eqc, int nu, const double* Q,
                             int64_t Q_bs, const double* R, int64_t R_bs, int N, const ccb_sim_opts* opts, double** d_Ku_out, int32_t* kexit,
-                            int32_t* iters) {
+                            int32_t* iters, int pipe_n = 0, double* const* pipe_tables = nullptr, long long pipe_off = 0) {
     const int nb = m->h.nb, ml = m->h.ml, n = 12 * nb;
     Scratch sc;
     double *d_zd, *d_Fd, *d_A, *d_Bu, *d_Bl, *d_G, *d_lam, *d_s, *d_Q, *d_R, *d_At, *d_D, *d_ws1, *d_ws2;
@@ -289,8 +292,34 @@ static int lqr_synth_device(ccb_mech* m, int device, int S, const double* zd, co
     pt.mark(1);
     if ((rc = project_linearisations(&m->h, device, S, nu, d_A, d_Bu, d_Bl, d_G, d_At, d_D, d_ws1, 0)) != CCB_OK) return bail(rc);
     pt.mark(2);
-    if ((rc = riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2,
-                                   0)) != CCB_OK) return bail(rc);
+    if (pipe_n > 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const size_t per = (size_t)(N - 1) * nu * n;
+        cudaStream_t ss = nullptr, sc2 = nullptr;
+        cudaEvent_t ev = nullptr;
+        auto done = [&](int r) { if (ev) cudaEventDestroy(ev); if (ss) cudaStreamDestroy(ss); if (sc2) cudaStreamDestroy(sc2); return r; };
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&sc2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+            return bail(done(cuda_fail(cudaGetLastError(), "peer pipeline set-up")));
+        const size_t wsd = riccati_sweep_ws_doubles(n, nu);
+        for (int g0 = 0; g0 < S; g0 += sms) {
+            const int gs = std::min(sms, S - g0);
+            rc = riccati_sweep_device(gs, n, nu, N, d_At + (size_t)g0 * n * n, d_D + (size_t)g0 * n * nu, 0, 0, (long long)n * n, (long long)n * nu,
+                                      d_Q + (size_t)g0 * Q_bs, Q_bs, d_R + (size_t)g0 * R_bs, R_bs, d_Ku + (size_t)g0 * per, d_kexit + g0, d_iters + g0,
+                                      d_ws2 + (size_t)g0 * wsd, ss);
+            if (rc != CCB_OK) { cudaDeviceSynchronize(); return bail(done(rc)); }
+            cudaEventRecord(ev, ss);
+            cudaStreamWaitEvent(sc2, ev, 0);
+            for (int i = 0; i < pipe_n; i++)
+                if (cudaMemcpyAsync(pipe_tables[i] + (size_t)(pipe_off + g0) * per, d_Ku + (size_t)g0 * per, (size_t)gs * per * sizeof(double), cudaMemcpyDefault,
+                                    sc2) != cudaSuccess) { cudaDeviceSynchronize(); return bail(done(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync(peer table)"))); }
+        }
+        const cudaError_t e1 = cudaStreamSynchronize(ss), e2 = cudaStreamSynchronize(sc2);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return bail(done(cuda_fail(e1 != cudaSuccess ? e1 : e2, "peer pipeline")));
+        done(0);
+    } else if ((rc = riccati_sweep_device(S, n, nu, N, d_At, d_D, 0, 0, (long long)n * n, (long long)n * nu, d_Q, Q_bs, d_R, R_bs, d_Ku, d_kexit, d_iters, d_ws2,
+                                          0)) != CCB_OK) return bail(rc);
     pt.mark(3);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaDeviceSynchronize"));
@@ -449,17 +478,25 @@ int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const doubl
     CCB_TRY(check_device(device, "ccb_lqr_synthesize_peers"));
     const int n = 12 * m->h.nb;
     const size_t per = (size_t)(N - 1) * nu * n;
-    const bool fused = riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA");     // K4 stores the rows into the tables itself
+    // K4 stores the rows into the tables itself (in-kernel peer stores under the recursion) when the shard is ONE wave of sweep CTAs -- there is
+    // nothing else to overlap the transfer with.  Larger shards sweep in groups of one wave and the copy engines move a finished group while the
+    // next one sweeps (measured r2 on 4 B200s, 256 Sawyer syntheses per rank: in-kernel stores 139 ms -- the remote stores of two waves of CTAs hold
+    // the sweeps up -- against 77 ms for synthesise + ncclAllGather; 2 GPUs 124 vs 135 ms; 8 GPUs, one wave, 43 vs 48 ms).
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const bool dmma = riccati_dmma_eligible(n, nu) && !getenv("CCB_NO_DMMA");
+    const bool fused = dmma && (S <= sms || getenv("CCB_PEER_INKERNEL"));
+    const bool piped = dmma && !fused;
     if (fused) {
         g_peer_tables.n = ntables;
         g_peer_tables.s_offset = s_offset;
         for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
     }
     double* d_Ku = nullptr;
-    int rc = lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters);
+    int rc = lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters, piped ? ntables : 0, tables, s_offset);
     g_peer_tables.n = 0;
     if (rc != CCB_OK) return rc;
-    if (!fused) {                      // other kernels: the finished shard is copied to every table (peer copies over NVLink)
+    if (!fused && !piped) {            // other kernels: the finished shard is copied to every table (peer copies over NVLink)
         for (int i = 0; i < ntables && rc == CCB_OK; i++)
             if (cudaMemcpy(tables[i] + (size_t)s_offset * per, d_Ku, (size_t)S * per * sizeof(double), cudaMemcpyDefault) != cudaSuccess)
                 rc = cuda_fail(cudaGetLastError(), "cudaMemcpy(peer table)");
