@@ -135,6 +135,17 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
             const char* pd = reinterpret_cast<const char*>(Dk - stride_t_D);
             for (size_t off = (size_t)tid * 128; off < (size_t)n * nu * sizeof(double); off += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + off));
         }
+        if (A_SM && stride_t_A != 0) {
+            // time-varying Ã (TrackingLQR) on the staged variant: this step's Ã_k streams into the third shared-memory matrix with cp.async
+            // while phase A runs, instead of being read fragment by fragment from L2 in phases B and D (r2 ncu of the time-varying sweep:
+            // long_scoreboard 2.0 stall cycles per issue).  Its last readers (phase D of the previous step) are behind a barrier.
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(Asm);
+            for (int e = tid; e < (n * n) / 2; e += NT) {
+                const int i = (2 * e) / n, j = 2 * e - i * n;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (unsigned)((i * LD + j) * sizeof(double))), "l"(Ak + (size_t)i * n + j));
+            }
+            asm volatile("cp.async.commit_group;");
+        }
         if (it == 1 || stride_t_D != 0) {
             for (int e = tid; e < n * 8; e += NT) { const int i = e >> 3, j = e & 7; Dp[e] = j < nu ? Dk[(size_t)i * nu + j] : 0.0; }
             __syncthreads();
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 }
                 DtP[j] = (a0 + a1) + (a2 + a3);
             }
+            if (A_SM && stride_t_A != 0) asm volatile("cp.async.wait_all;");
             __syncthreads();
             const size_t lda = A_SM ? (size_t)LD : (size_t)n;
             const double* Ab = A_SM ? Asm : Ak;
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
                 if (col < n) DtP[g * LD + col] = c0 + e0;
                 if (col + 1 < n) DtP[g * LD + col + 1] = c1 + e1;
             }
+            if (A_SM && stride_t_A != 0) asm volatile("cp.async.wait_all;");
             __syncthreads();
             // ---- (B) rhs = D'P Ã (tile column w; Ã from global) and Sc = R + D'P D (warp 0)
             {
@@ -433,7 +446,7 @@ int riccati_sweep_dmma_device(int S, int n, int nu, int N, const double* At, con
     if (k_hi <= 0) { k_hi = N - 1; k_lo = 1; resume = 0; }
     const bool stage = stride_t_A == 0 && n <= 36;       // small time-invariant problems: Ã, Q, previous P in shared memory as well
     const bool stage_a = !stage && n >= 72 && dmma_smem_bytes(n, T, 1) <= 227 * 1024;
-    const bool stage_b = stage_a && stride_t_A == 0;     // ... and, when Ã does not change, Ã in that third matrix with the previous P of my tiles in registers   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
+    const bool stage_b = stage_a && (stride_t_A == 0 || !getenv("CCB_K4_TV_STAGE1"));     // ... and, when Ã does not change, Ã in that third matrix with the previous P of my tiles in registers   // 72 <= n <= 84: previous P in shared memory (for smaller n the extra shared memory costs more residency than it saves)
 #define CCB_DMMA_ARGS S, n, nu, N, At, D, stride_t_A, stride_t_D, stride_s_A, stride_s_D, Q, Q_bs, R, R_bs, Ku, kexit, iters, ws, ws_stride, stream, k_hi, k_lo, resume
 #define CCB_DMMA_CASE(TT)                                                                      \
     case TT:                                                                                   \
