@@ -123,6 +123,18 @@ def test_peer_gain_tables_two_ranks(cc):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("table == gathered: True") == 2
+    # a shard of more than one wave of sweep CTAs (200 Sawyer syntheses per rank): the group-pipelined copy-engine exchange
+    cmd = cmd[:-4] + [os.path.join(root, "tools", "peer_check.py"), "sawyer", "400", "120"]
+    cmd[cmd.index("29541")] = "29542"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("table == gathered: True") == 2 and r.stdout.count("peer-written slice == local synthesis: True") == 2
+    # TrackingLQR tables of 8 Sawyer trajectories sharded over the two ranks (in-kernel peer stores), refilled once
+    cmd = cmd[:-4] + [os.path.join(root, "tools", "peer_tracking_check.py"), "8", "300"]
+    cmd[cmd.index("29542")] = "29543"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("tables bit-identical across ranks: True") == 2
 
 
 def test_record_pipeline_is_bit_identical_to_one_launch(cc, monkeypatch):

@@ -30,6 +30,7 @@ if world > 1: dist.barrier()
 t0 = time.time()
 tab = cc.dist.PeerTrackingTable(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"], device=local)
 t_f = time.time() - t0
+tab.refill()                    # synthesise again into the mapped tables (allocation + IPC mappings kept)
 full = tab.read()
 tl = cc.TrackingLQR(mech, sto, U, cfg["eqcids"], cfg["Q"], cfg["R"], device=local)          # everything locally
 ok_k = np.array_equal(tab.kexit, tl.kexit)
