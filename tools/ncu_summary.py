@@ -12,7 +12,10 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
         "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_dmma.sum",
-        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_shfl.sum", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed_op_shfl.sum", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_op_global_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "smsp__inst_executed_op_global_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "lts__t_sectors_op_write.sum", "lts__t_sectors_op_read.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     for k in KEYS:
