@@ -1,12 +1,12 @@
 """Randomised parity sweep of the rollout path (GPU through the C-ABI vs the CPU oracle).
 
-    python tools/fuzz_parity.py [ncases] [seed] > profiles/fuzz_r2.jsonl
+    python tests/fuzz_parity.py [ncases] [seed] > profiles/fuzz_r2.jsonl
 
 Every case draws a mechanism, a control law, a batch size around the kernels' quantisation edges (warp fill, persistent-launch
 thresholds), a step count, a kernel variant (`lanes`), recording on/off and whether the rollout is issued as one call or as two
 consecutive calls (resume from the stored state / multipliers / step index).  It prints one JSON line per case: max relative error of
 the final states (and of the recorded trajectory), and whether the per-system newton! iteration totals equal the oracle's.  The oracle
-is the checker here (tools/ is test infrastructure, not the product path).
+is the checker here (test infrastructure, not the product path).
 """
 import json, math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,11 +1,11 @@
 """Randomised parity sweep of the constrained Riccati recursion (GPU `dlqr` through the C-ABI vs the CPU oracle).
 
-    python tools/fuzz_synth.py [ncases] [seed] > profiles/fuzz_synth_r2.jsonl
+    python tests/fuzz_synth.py [ncases] [seed] > profiles/fuzz_synth_r2.jsonl
 
 Random state / input / constraint dimensions across the kernel-selection boundaries (K3 FMA sweep, K4 DMMA sweep with its staged
 variants and the scalar-input path, K4b blocked sweep for n > 108), random horizons including the shortest ones (N = 2: one gain row) and
 random batch sizes.  One JSON line per case: worst element-relative gain error (tests/helpers.gain_err), whether the break index and the
-iteration count equal the oracle's.  The oracle is the checker (tools/ is test infrastructure, not the product path).
+iteration count equal the oracle's.  The oracle is the checker (test infrastructure, not the product path).
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,14 +1,10 @@
-"""Randomised GPU-vs-oracle sweeps (tools/fuzz_parity.py, tools/fuzz_synth.py) at sizes that finish in seconds: random mechanism / law /
+"""Randomised GPU-vs-oracle sweeps (tests/fuzz_parity.py, tests/fuzz_synth.py) at sizes that finish in seconds: random mechanism / law /
 batch / steps / kernel variant / record / resumed-call combinations of the rollout path, and random (n, nu, m_lambda, N, batch) Riccati
 recursions across the kernel-selection boundaries.  Tolerance 1e-9 (north_star); failure flags, break indices and iteration counts exact.
 The 200- and 150-case runs of round 2 are on file in profiles/fuzz_r2.jsonl and profiles/fuzz_synth_r2.jsonl."""
-import os
-import sys
-
 import pytest
 
 pytestmark = pytest.mark.gpu
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
 
 @pytest.mark.parametrize("seed", [21, 22])
