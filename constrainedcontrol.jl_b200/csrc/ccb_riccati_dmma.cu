@@ -73,11 +73,17 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
     // 128 CTAs x 8 tables of ~10 GB touch more 2 MB pages than the TLB holds.)
     constexpr int kPeerFlush = 64;
     int flush_hi = k_hi;                                      // rows k-1 for k in (.., flush_hi] are not pushed yet
+    // The CTAs of a launch iterate in step, and so do the launches of the other GPUs: with one flush phase and one peer order for everybody the
+    // traffic would come in bursts of gridDim.x runs aimed at ONE table at a time.  Each CTA therefore starts with a first run of its own length
+    // (its flushes then fall on different iterations than its neighbours') and walks the tables from its own starting peer.
+    int flush_len = (peers.n > 0 && peers.spread) ? 1 + (int)((s * 29) % kPeerFlush) : kPeerFlush;
+    const int peer0 = (peers.n > 0 && peers.spread) ? (int)((s + (size_t)(peers.s_offset / gridDim.x) + 1) % peers.n) : 0;
     auto peer_flush = [&](int k_from) {                       // push rows (k_from - 1) .. (flush_hi - 1); all threads, after a barrier
         if (peers.n == 0 || flush_hi < k_from) return;
         const size_t off = (size_t)(k_from - 1) * nu * n, cnt2 = (size_t)(flush_hi - k_from + 1) * nu * n / 2;
         const double2* src = reinterpret_cast<const double2*>(Kout + off);
-        for (int pt = 0; pt < peers.n; pt++) {
+        for (int pi = 0; pi < peers.n; pi++) {
+            const int pt = (pi + peer0) % peers.n;
             double2* dst = reinterpret_cast<double2*>(peers.t[pt] + kbase + off);
             for (size_t e = tid; e < cnt2; e += NT) dst[e] = src[e];
         }
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         }
         __syncthreads();
         if (brk) break;
-        if (flush_hi - k + 1 >= kPeerFlush) peer_flush(k);
+        if (flush_hi - k + 1 >= flush_len) { peer_flush(k); flush_len = kPeerFlush; }
     }
     if (k < k_lo && k_lo > 1) {
         peer_flush(k_lo);                                          // this launch's part is done, the sweep is not: park P for the next launch

@@ -32,7 +32,7 @@ int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const do
 bool riccati_dmma_eligible(int n, int nu);
 }
 using namespace ccb;
-namespace ccb { thread_local PeerTables g_peer_tables = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0, 0}; }
+namespace ccb { thread_local PeerTables g_peer_tables = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0, 0, 1}; }
 
 namespace {
 
@@ -490,6 +490,7 @@ int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const doubl
     if (fused) {
         g_peer_tables.n = ntables;
         g_peer_tables.s_offset = s_offset;
+        g_peer_tables.spread = getenv("CCB_PEER_NO_SPREAD") ? 0 : 1;
         for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
     }
     double* d_Ku = nullptr;
@@ -754,6 +755,7 @@ int ccb_tracking_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, int32_
     const bool fused = riccati_dmma_eligible(12 * m->h.nb, nu) && !getenv("CCB_NO_DMMA");
     g_peer_tables.n = fused ? ntables : 0;
     g_peer_tables.s_offset = s_offset;
+    g_peer_tables.spread = getenv("CCB_PEER_NO_SPREAD") ? 0 : 1;
     for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
     const int rc = tracking_synth_device(m, device, S, N, traj, Ftau, eqc, nu, Q, R, opts, nullptr, nullptr, nullptr, nullptr, kexit, iters,
                                          fused ? 0 : ntables, tables);
