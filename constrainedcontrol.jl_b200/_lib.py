@@ -50,7 +50,7 @@ SYMBOLS = [
     "ccb_batch_create", "ccb_batch_destroy", "ccb_batch_set_state", "ccb_batch_get_state", "ccb_batch_device_ptrs", "ccb_ctrl_create",
     "ccb_ctrl_destroy", "ccb_ctrl_pid_state", "ccb_simulate", "ccb_simulate_device", "ccb_batch_sync", "ccb_batch_stream", "ccb_launch_count",
     "ccb_linearize", "ccb_dlqr", "ccb_lqr_synthesize", "ccb_tracking_synthesize", "ccb_synth_phase_ms", "ccb_lqr_create", "ccb_ctrl_get_gains", "ccb_tracking_create", "ccb_ctrl_set_replication",
-    "ccb_are_solve", "ccb_scratch_release", "ccb_gains_alloc", "ccb_gains_open", "ccb_gains_close", "ccb_gains_free", "ccb_gains_read",
+    "ccb_are_solve", "ccb_scratch_release", "ccb_gains_alloc", "ccb_gains_open", "ccb_gains_close", "ccb_gains_free", "ccb_gains_read", "ccb_gains_defer_backfill", "ccb_gains_backfill",
     "ccb_lqr_synthesize_peers", "ccb_tracking_synthesize_peers", "ccb_lqr_ctrl_from_table", "ccb_tracking_ctrl_from_table",
 ]
 

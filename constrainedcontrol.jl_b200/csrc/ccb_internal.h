@@ -169,7 +169,9 @@ bool mw_kernel_eligible(const DevMech& M);
 // peer GPUs' tables mapped through CUDA IPC); system s of the launch goes to index s_offset + s of every table.  The all-gather of
 // SURVEY 8(e) fused into the sweep: the rows leave over NVLink while the recursion runs.  Set for the calling thread by
 // ccb_lqr_synthesize_peers (ccb_synth.cu), read by the K4 launcher; n == 0: none.
-struct PeerTables { double* t[8]; int n; long long s_offset; int spread; };   // spread: stagger the CTAs' flush phases and rotate their peer order
+struct PeerTables { double* t[8]; int n; long long s_offset; int spread; int defer_backfill; };
+// spread: stagger the CTAs' flush phases and rotate their peer order.  defer_backfill: push only the rows the recursion produced (k >= kexit); the
+// rows below the break index (copies of row kexit - 1, lqr.jl:179-181) are written by every GPU into its own table afterwards (ccb_gains_backfill)
 extern thread_local PeerTables g_peer_tables;
 // K5 (ccb_are.cu): kind 0 DARE, 1 CARE; device pointers; ws >= S * are_ws_doubles(n) doubles
 size_t are_ws_doubles(int n);

@@ -410,6 +410,14 @@ __global__ void __launch_bounds__(32 * T, (NU1 && T <= 8) ? (K4_MINB_NUM / T > 0
         return;
     }
     if (k < 1) k = 1;                                                    // a completed loop leaves k == 1
+    if (peers.n > 0 && peers.defer_backfill) {
+        // multi-GPU exchange with deferred back-fill: only the rows the recursion produced cross NVLink; every GPU replicates row k - 1 below the
+        // break index in its OWN table after the exchange barrier (ccb_gains_backfill) -- for the Sawyer arm at N = 2000 that is a fifth of the
+        // table, and it used to leave all the CTAs of all the GPUs in one burst at the end of the sweep, with nothing left to hide it under
+        peer_flush(k);
+        if (tid == 0) { kexit[s] = k; iters[s] = (resume ? iters[s] : 0) + it; }
+        return;
+    }
     for (int k2 = k - 1; k2 >= 1; k2--) {                                // lqr.jl:179-181 back-fill
         for (int e = tid; e < nu * n; e += NT) Kout[(size_t)(k2 - 1) * nu * n + e] = Kout[(size_t)k2 * nu * n + e];
         __syncthreads();

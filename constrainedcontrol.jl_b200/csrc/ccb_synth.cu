@@ -32,7 +32,8 @@ int riccati_sweep_device(int S, int n, int nu, int N, const double* At, const do
 bool riccati_dmma_eligible(int n, int nu);
 }
 using namespace ccb;
-namespace ccb { thread_local PeerTables g_peer_tables = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0, 0, 1}; }
+namespace ccb { thread_local PeerTables g_peer_tables = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, 0, 0, 1, 0}; }
+static thread_local int g_defer_backfill = 0;     // ccb_gains_defer_backfill
 
 namespace {
 
@@ -459,6 +460,54 @@ int ccb_gains_free(double* dptr) {
     return CCB_OK;
 }
 
+namespace {
+// rows 0 .. kexit[s] - 2 of system s <- row kexit[s] - 1 (lqr.jl:179-181), 16-byte stores; grid (S, row chunks)
+__global__ void gains_backfill_kernel(double* __restrict__ table, const int* __restrict__ kexit, long long per, int row) {
+    const int s = blockIdx.x, k = kexit[s];
+    if (k <= 1) return;
+    double* base = table + (size_t)s * per;
+    const double2* src = reinterpret_cast<const double2*>(base + (size_t)(k - 1) * row);
+    const int row2 = row / 2;
+    for (int r = blockIdx.y; r < k - 1; r += gridDim.y) {
+        double2* dst = reinterpret_cast<double2*>(base + (size_t)r * row);
+        for (int e = threadIdx.x; e < row2; e += blockDim.x) dst[e] = src[e];
+    }
+}
+}  // namespace
+
+int ccb_gains_defer_backfill(int32_t on) {
+    g_defer_backfill = on ? 1 : 0;
+    return CCB_OK;
+}
+
+int ccb_gains_backfill(int32_t device, double* table, int64_t S, int32_t N, int32_t nu, int32_t n, const int32_t* kexit) {
+    if (!table || !kexit || S < 0 || N < 2 || nu < 1 || n < 1) { set_error("ccb_gains_backfill: bad arguments"); return CCB_E_INVALID; }
+    CCB_TRY(check_device(device, "ccb_gains_backfill"));
+    if (S == 0) return CCB_OK;
+    for (int64_t s = 0; s < S; s++)
+        if (kexit[s] < 1 || kexit[s] > N - 1) { set_error("ccb_gains_backfill: kexit[" + std::to_string(s) + "] = " + std::to_string(kexit[s]) + " outside 1 .. N-1"); return CCB_E_INVALID; }
+    const int row = nu * n;
+    int* d_k = nullptr;
+    CCB_CUDA(cudaMalloc(&d_k, (size_t)S * sizeof(int)));
+    cudaError_t e = cudaMemcpy(d_k, kexit, (size_t)S * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (row % 2 == 0) {
+            gains_backfill_kernel<<<dim3((unsigned)S, 16), 256>>>(table, d_k, (long long)(N - 1) * row, row);
+            g_launches++;
+            e = cudaGetLastError();
+        } else {                     // odd row length (nu n odd): rows are not 16-byte aligned, copy them one by one
+            const size_t per = (size_t)(N - 1) * row;
+            for (int64_t s = 0; s < S && e == cudaSuccess; s++)
+                for (int r = 0; r < kexit[s] - 1 && e == cudaSuccess; r++)
+                    e = cudaMemcpyAsync(table + s * per + (size_t)r * row, table + s * per + (size_t)(kexit[s] - 1) * row, (size_t)row * sizeof(double), cudaMemcpyDeviceToDevice, 0);
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_k);
+    if (e != cudaSuccess) return cuda_fail(e, "ccb_gains_backfill");
+    return CCB_OK;
+}
+
 int ccb_gains_read(int32_t device, const double* dptr, int64_t offset, double* host, int64_t count) {
     if (!dptr || !host || count < 0 || offset < 0) { set_error("ccb_gains_read: bad arguments"); return CCB_E_INVALID; }
     CCB_TRY(check_device(device, "ccb_gains_read"));
@@ -491,11 +540,13 @@ int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const doubl
         g_peer_tables.n = ntables;
         g_peer_tables.s_offset = s_offset;
         g_peer_tables.spread = getenv("CCB_PEER_NO_SPREAD") ? 0 : 1;
+        g_peer_tables.defer_backfill = g_defer_backfill;
         for (int i = 0; i < ntables; i++) g_peer_tables.t[i] = tables[i];
     }
     double* d_Ku = nullptr;
     int rc = lqr_synth_device(m, device, S, zd, Fd, eqc, nu, Q, Q_bs, R, R_bs, N, opts, &d_Ku, kexit, iters, piped ? ntables : 0, tables, s_offset);
     g_peer_tables.n = 0;
+    g_peer_tables.defer_backfill = 0;
     if (rc != CCB_OK) return rc;
     if (!fused && !piped) {            // other kernels: the finished shard is copied to every table (peer copies over NVLink)
         for (int i = 0; i < ntables && rc == CCB_OK; i++)

@@ -223,14 +223,46 @@ class PeerGainTable:
             self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
 
         self._run_shard = run_shard
-        _peer_fill(self, device, S * self.per, run_shard)
+        self._fill()
+
+    def _fill(self):
+        """one exchange: the sweeps push the rows they computed into every table (_peer_fill), then -- the break indices of all systems being
+        known everywhere -- every rank replicates the rows below each break index in its OWN table (lqr.jl:179-181 back-fill; a fifth of a
+        Sawyer table at N = 2000 that therefore never crosses NVLink).  A second agreement closes the fill: nobody starts the next exchange
+        (whose stores would land in a table still being completed) before every rank is done, and a failure reaches every rank."""
+        import ctypes as C
+        import time
+        from . import _lib
+        from ._lib import check, ptr
+        L = _lib.lib()
+        world, rank = _world()
+        L.ccb_gains_defer_backfill(C.c_int32(1 if world > 1 else 0))
+        try:
+            _peer_fill(self, self.device, self.S * self.per, self._run_shard)
+        finally:
+            L.ccb_gains_defer_backfill(C.c_int32(0))
+        if world > 1:
+            t0 = time.time()
+            err = None
+            try:
+                check(L.ccb_gains_backfill(C.c_int32(self.device), self.ptr, C.c_int64(self.S), C.c_int32(self.N), C.c_int32(self.nu), C.c_int32(self.n),
+                                           ptr(self.kexit)))
+            except Exception as e:  # noqa: BLE001 -- carried to the agreement
+                err = e
+            if not _agree(err is None, self.device):
+                _peer_unmap(self)
+                if self.ptr:
+                    L.ccb_gains_free(self.ptr); self.ptr = None
+                raise PeerProtocolError(f"gain-table back-fill failed on rank {rank}: {err!r}" if err is not None
+                                        else "gain-table back-fill failed on another rank") from err
+            self.timing["backfill_s"] = time.time() - t0
 
     def refill(self):
         """synthesise again into the SAME tables (allocation and IPC mappings are kept): the steady-state cost of the exchange.  Collective."""
         if self._ctrl is not None:
             self._ctrl.invalidate(); self._ctrl = None
         self.kexit[:] = 0; self.iters[:] = 0
-        _peer_fill(self, self.device, self.S * self.per, self._run_shard)
+        self._fill()
         return self
 
     def read(self, s0: int = 0, count: int = None) -> np.ndarray:
@@ -303,7 +335,11 @@ class PeerTrackingTable:
             self.kexit[lo:hi] = kx; self.iters[lo:hi] = it
 
         self._run_shard = run_shard
-        _peer_fill(self, device, S * self.per, run_shard)
+        self._fill()
+
+    def _fill(self):
+        # the time-varying recursion has no early break (lqr_tracking.jl:87-115): every row is computed and pushed, nothing to back-fill
+        _peer_fill(self, self.device, self.S * self.per, self._run_shard)
 
     refill = PeerGainTable.refill
     read = PeerGainTable.read

@@ -251,6 +251,14 @@ int ccb_gains_open(int32_t device, const unsigned char ipc_handle[64], double** 
 int ccb_gains_close(double* dptr);
 int ccb_gains_free(double* dptr);
 int ccb_gains_read(int32_t device, const double* dptr, int64_t offset, double* host, int64_t count);
+/* Deferred back-fill of the exchange (optional).  dlqr fills the rows below its break index with copies of the last row it computed
+ * (reference src/control/lqr.jl:179-181: `for k2 = k-1:-1:1  Ku[k2] = Ku[k2+1]`); for the Sawyer arm at N = 2000 that is a fifth of every
+ * table, and there is no reason to send copies over NVLink.  After ccb_gains_defer_backfill(1) the ccb_lqr_synthesize_peers calls of
+ * this thread push only the rows the recursion produced (k >= kexit) when the sweep itself does the stores; once the exchange barrier has
+ * passed and the break indices of ALL systems are known on every rank, each rank completes its own table with ccb_gains_backfill
+ * (kexit: host, [S], values 1 .. N-1 as returned by the synthesis; idempotent on a table that is already complete). */
+int ccb_gains_defer_backfill(int32_t on);
+int ccb_gains_backfill(int32_t device, double* table, int64_t S, int32_t N, int32_t nu, int32_t n, const int32_t* kexit);
 int ccb_lqr_synthesize_peers(ccb_mech* m, int32_t device, int32_t S, const double* zd, const double* Fd, const int32_t* eqc, int32_t nu,
                              const double* Q, int64_t Q_bstride, const double* R, int64_t R_bstride, int32_t N, const ccb_sim_opts* opts,
                              int32_t ntables, double* const* tables, int64_t s_offset, int32_t* kexit, int32_t* iters);

@@ -174,3 +174,13 @@ def test_shard_range_covers_everything():
             assert cuts[0][0] == 0 and cuts[-1][1] == total
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
+
+
+def test_peer_tables_share_refill_but_not_fill():
+    """PeerTrackingTable borrows refill / read / free from PeerGainTable; each class brings its own _fill (the LQR table completes the rows below
+    the break index locally after the exchange, the tracking recursion has no break)"""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import ccb200 as cc
+    g, t = cc.dist.PeerGainTable, cc.dist.PeerTrackingTable
+    assert t.refill is g.refill and t.read is g.read and t.free is g.free
+    assert callable(g._fill) and callable(t._fill) and t._fill is not g._fill
