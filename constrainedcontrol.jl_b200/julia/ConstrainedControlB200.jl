@@ -381,5 +381,10 @@ function synthesize_peers!(mh::MechHandle, zd::Array{Float64,3}, Fτd::Matrix{Fl
                 mh.ptr, device, S, zd, Fτd, eqcidx, nu, permutedims(Qd), 0, permutedims(Rd), 0, N, C_NULL, length(tables), tables, s_offset, kexit, iters))
     return kexit, iters
 end
+# Optional: keep the rows below the break index (copies, lqr.jl:179-181) off NVLink.  defer_backfill!(true) before synthesize_peers!, then -- after the
+# barrier, with the break indices of ALL systems gathered -- gains_backfill!(t, kexit_all, N, nu, n) on every rank's own table, then a second barrier.
+defer_backfill!(on::Bool) = check(ccall((:ccb_gains_defer_backfill, libccb), Cint, (Int32,), on ? 1 : 0))
+gains_backfill!(t::Ptr{Float64}, kexit::Vector{Int32}, N::Integer, nu::Integer, n::Integer; device = 0) =
+    check(ccall((:ccb_gains_backfill, libccb), Cint, (Int32, Ptr{Float64}, Int64, Int32, Int32, Int32, Ptr{Int32}), device, t, length(kexit), N, nu, n, kexit))
 
 end # module
