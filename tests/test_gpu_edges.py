@@ -230,3 +230,28 @@ def test_persistent_launch_of_the_long_chain_kernel_is_bit_identical(cc, monkeyp
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
         assert np.all(a[2] > 0)
+
+
+def test_gains_backfill_completes_rows_below_the_break_index(cc):
+    """ccb_gains_backfill (deferred back-fill of the multi-GPU exchange): rows 0 .. kexit-2 of every system become copies of row kexit-1
+    (lqr.jl:179-181), everything else is untouched; break indices outside 1 .. N-1 are refused"""
+    import ctypes as C
+    import torch
+    from ccb200 import _lib
+    L = _lib.lib()
+    for nu, n in ((2, 12), (7, 84), (1, 3)):          # even rows (16-byte kernel) and an odd row length (copy path)
+        S, N = 5, 9
+        row = nu * n
+        ref = np.arange(S * (N - 1) * row, dtype=np.float64).reshape(S, N - 1, row)
+        t = torch.from_numpy(ref.copy()).cuda()
+        kexit = np.array([1, 3, 8, 2, 5], np.int32)
+        _lib.check(L.ccb_gains_backfill(C.c_int32(0), C.c_void_p(t.data_ptr()), C.c_int64(S), C.c_int32(N), C.c_int32(nu), C.c_int32(n), _lib.ptr(kexit)))
+        out = t.cpu().numpy()
+        for s in range(S):
+            k = int(kexit[s])
+            assert np.array_equal(out[s, k - 1:], ref[s, k - 1:])
+            for r in range(k - 1):
+                assert np.array_equal(out[s, r], ref[s, k - 1])
+    bad = np.array([1, 0, 8, 2, 5], np.int32)
+    with pytest.raises(_lib.CcbError):
+        _lib.check(L.ccb_gains_backfill(C.c_int32(0), C.c_void_p(t.data_ptr()), C.c_int64(5), C.c_int32(9), C.c_int32(1), C.c_int32(3), _lib.ptr(bad)))
