@@ -113,6 +113,27 @@ def test_open_loop_table_and_recording(cc, orc):
     assert np.array_equal(storage.x[0][0], st0[0, 0, 0:3])   # Storage[1] is the initial continuous state
 
 
+@pytest.mark.parametrize("lanes", [0, 6, 1, 16])   # auto (K1r: 4 joints = 20 lanes), K1m, K1c, general kernel K1
+def test_reference_U_swings_the_triple_cartpole_up(cc, orc, lanes):
+    """the reference's only numeric fixture played open loop for its full 1000 steps (examples/trackingLQR_triple_cartpole.jl:45-53): the CUDA path
+    ends with all three poles upright like the oracle does (tests/test_oracle_reference_fixture.py: the known answer that checks the restated
+    dynamics against the dynamics upstream optimised U on) and agrees with the oracle along the whole swing-up"""
+    mech, cfg = cc.examples.triple_cartpole()
+    U = np.load(__file__.replace("test_gpu_rollout.py", "golden/triple_cartpole_U.npy")).reshape(1000, 1)
+    om = orc.OracleMech(mech.desc())
+    st0 = mech.state_vector()[None]
+    ref = om.simulate(st0, 1000, ctrl=om.make_ctrl(1, kind="table", eqc=[0], U=U), record=True)
+    ol = cc.OpenLoop(mech, cfg["eqcids"], U)
+    storage, final, status = cc.simulate(mech, 10.0, ol, record=True, states=st0, lanes=lanes, return_status=True)
+    assert status[0] > 0
+    last = storage.data[-1, 0]                                  # Storage[1000]: the state at the start of the last step
+    ang = 2 * np.arctan2(last[1:, 4], last[1:, 3])
+    assert np.abs(np.mod(ang, 2 * math.pi) - math.pi).max() < 0.01 and abs(last[0, 1]) < 0.01
+    assert np.abs(last[1:, 2] - [0.5, 1.5, 2.5]).max() < 1e-4
+    assert rel_err(storage.data, ref["storage"]) < TOL
+    assert rel_err(final, ref["states"]) < TOL
+
+
 def test_shared_goal_pid_built_for_one_system_runs_a_batch(cc, orc):
     """ADVICE r1 (ccb_api.cu): the Julia shim's BatchPID with goals (nu,1) creates the controller with B = 1 / goal_bstride = 0 and then
     simulates a larger batch.  The per-system integrator state must be re-sized to the batch (it used to be indexed out of bounds); a
