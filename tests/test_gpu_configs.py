@@ -201,6 +201,9 @@ def test_c5_deltabot_closed_chain(cc, orc):
     assert np.all(status > 0) and np.all(r["iters"] > 0)
     assert rel_err(sto.data, r["storage"]) < 1e-9        # (measured 1e-13: the same regularisation in both implementations)
     assert np.abs(fin[0, 4, 0:3] - st0[0, 4, 0:3]).max() < 5e-3   # the feed-forward holds the platform (nearly) in place
+    # the reference's 8-digit literal IS the equilibrium torque of the step map (tests/test_oracle_reference_fixture.py: the restatement's own
+    # equilibrium is 6.78794845...): one step from rest leaves every body at rest to 1e-8, without it the bodies move at 0.16 m/s
+    assert np.abs(sto.data[1, 0, :, 7:13]).max() < 1e-8
 
 
 def test_c5_deltabot_lqr_from_the_example_grid(cc, orc):

@@ -1,5 +1,6 @@
-"""The oracle against the reference's ONLY numeric fixture: the input sequence `U` of
-examples/trackingLQR_triple_cartpole.jl:1 (identical copy in test/examples/), committed as tests/golden/triple_cartpole_U.npy.
+"""The oracle against the numbers the reference owns: its one numeric fixture, the input sequence `U` of
+examples/trackingLQR_triple_cartpole.jl:1 (identical copy in test/examples/), committed as tests/golden/triple_cartpole_U.npy, and the
+gravity-compensation literal of examples/lqr_deltabot.jl:53 (last test).
 
 `U` is a swing-up of the triple pendulum on a cart that upstream computed on ITS dynamics (ConstrainedDynamics.jl): the example plays it
 open loop (`simulate!(mech, storage0, control!, record = true)` with `setForce!(mechanism, joint1, [U[k]])`, :45-53) from the hanging
@@ -88,3 +89,32 @@ def test_what_the_fixture_pins(cc, orc, what, bound):
     sto = _swing_up(cc, orc, mech, U, 1000)
     _, dphi, _ = _upright_error(sto[-1])
     assert np.abs(dphi).max() > bound, (what, dphi)
+
+
+def _deltabot_velocity_after_one_step(om, st0, eqc, u):
+    ctrl = om.make_ctrl(1, kind="table", eqc=eqc, U=np.asarray(u, dtype=float).reshape(1, 2))
+    return om.simulate(st0, 1, ctrl=ctrl, eps=1e-13)["states"][0][:, 7:13].ravel()
+
+
+def test_deltabot_gravity_compensation_constant(cc, orc):
+    """the reference's second numeric literal: `Fτd = [[[6.7879484]];[[-6.7879484]]]` (examples/lqr_deltabot.jl:53), the joint torques that hold the
+    closed-chain deltabot at the example's pose against gravity (the LQR linearises about that equilibrium).  The restatement's own equilibrium
+    torques -- the inputs for which one step from rest leaves every body at rest, found by Newton on the step map -- agree with the literal in all
+    eight printed digits; statics of a closed chain, so this pins masses, geometry, joint vertices, g = 9.81 and the sign / axis convention of
+    `setForce!` on a revolute joint between two moving bodies at the 1e-8 level."""
+    mech, cfg = cc.examples.deltabot()
+    om = orc.OracleMech(mech.desc())
+    st0 = mech.state_vector()[None]
+    eqc = [mech.eqc_index(i) for i in cfg["eqcids"]]
+    assert np.abs(_deltabot_velocity_after_one_step(om, st0, eqc, [0.0, 0.0])).max() > 0.1          # it falls without the torques
+    assert np.abs(_deltabot_velocity_after_one_step(om, st0, eqc, [6.7879484, -6.7879484])).max() < 1e-8   # the reference's literal holds it
+    u = np.array([6.0, -6.0])
+    for _ in range(5):
+        a = _deltabot_velocity_after_one_step(om, st0, eqc, u)
+        h = 1e-4
+        B = np.stack([(_deltabot_velocity_after_one_step(om, st0, eqc, u + [h, 0.0]) - a) / h,
+                      (_deltabot_velocity_after_one_step(om, st0, eqc, u + [0.0, h]) - a) / h], axis=1)
+        u = u + np.linalg.lstsq(B, -a, rcond=None)[0]
+    assert np.abs(_deltabot_velocity_after_one_step(om, st0, eqc, u)).max() < 1e-11
+    assert abs(u[0] + u[1]) < 1e-9                                                                  # mirror symmetry of the two legs
+    assert abs(u[0] - 6.7879484) < 1e-7 and int(u[0] * 1e7) == 67879484                             # 6.78794845...: every printed digit
