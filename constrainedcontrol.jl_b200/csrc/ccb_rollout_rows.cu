@@ -39,9 +39,9 @@ struct RowsOrder { int joint[6]; };
 #ifndef K1R_MAXREG
 #define K1R_MAXREG 168
 #endif
-// the persistent variant runs exactly two warps per scheduler: up to 248 registers fit (8 x 32 x 248 <= 64 K)
+// the persistent variant runs at most two warps per scheduler: all 255 registers fit (8 x 32 x 256 = 64 K)
 #ifndef K1R_PERSIST_MAXREG
-#define K1R_PERSIST_MAXREG 248
+#define K1R_PERSIST_MAXREG 255
 #endif
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -138,11 +138,13 @@ __global__ void __maxnreg__(PERSIST ? K1R_PERSIST_MAXREG : K1R_MAXREG) rollout_r
             if (j >= extra) continue;
             trip = nworkers + j;
             if (chunk > 0) {
-                if (wl == 0) {
-                    const volatile int* flag = A.persist + 1 + trip;
-                    while (*flag < chunk) __nanosleep(2000);
-                }
-                __syncwarp();
+                // Every lane polls the same word (one broadcast load) and the exit is a warp VOTE, so the wait is warp-uniform by construction.
+                // A lane-0-only spin (`if (wl == 0) while (*flag < chunk) ...; __syncwarp()`) made ptxas give up on proving the warp converged
+                // for the rest of the kernel: every later shfl.sync got a BRA.DIV-guarded slow path -- 804 instead of 402 SHFL, 1934 instead of
+                // 312 MOV, 7888 instead of 4496 instructions in the cartpole instantiation -- and the persistent launch ran 7 % slower per warp
+                // than the plain kernel at the same register count (3552 systems: 24.7 against 23.1 ms).
+                const volatile int* flag = A.persist + 1 + trip;
+                while (!__all_sync(0xffffffffu, *flag >= chunk)) __nanosleep(2000);
                 __threadfence();
             }
         }
@@ -649,25 +651,41 @@ int launch_rollout_rows(const DevMech& M, const DevCtrl& C, const SimArgs& a_in,
     int grid = (a_in.B + spw - 1) / spw;
     size_t smem = (size_t)(spw * M.nj * kGS + M.nj * kCS + spw * M.nj * 17) * sizeof(double);
     SimArgs a = a_in;
-    // Persistent time-sliced launch (see the work loop in the kernel): when the batch needs more one-warp CTAs than two per SM sub-partition but
-    // fewer than 1.2x that many, a plain launch runs at the three-warp time T(3) while persistent warps at two per scheduler need about
-    // T(2) * W / slots.  Measured on 2000 cartpole steps (tools/persist_probe.py): 4096 systems (W = 1.15 slots) 29.7 ms against 31.7 ms plain;
-    // 4400 systems (1.24 slots) 31.8 against 32.1 ms: break-even.  Not for laws with controller state on the device (PID).
+    // Two launches of the 255-register (spill-free) instantiation, which holds at most two one-warp CTAs per scheduler (slots2 = 8 per SM):
+    //  * whole: the batch needs no more than slots2 warps anyway -- one chunk, no extra triples, i.e. the plain kernel's code without its
+    //    168-register cap and its 300 bytes of spills.  2000 cartpole steps (tools/persist_probe4.py): 512 systems 17.7 against 19.6 ms, 2048:
+    //    22.0 / 23.9, 3552: 22.4 / 24.3; pendulum 4096 x 1000: 9.3 / 10.0; triple cartpole 1184 x 1000: 20.4 / 22.5.
+    //  * time-sliced: between 1x and 1.35x slots2 warps a plain launch runs at the three-warps-per-scheduler time T(3) with a good part of the
+    //    third-warp slots empty; slots2 persistent workers cut the rollout into chunks of steps and share the extra triples on a static rotating
+    //    schedule (work loop in the kernel): about T(2) x warps / slots2.  4096 cartpoles (1.15 slots2) 26.3 against 31.7 ms plain, 4400: 28.3 /
+    //    31.9, 4800 (1.35): 30.7 / 31.7, 5328 (1.5): 34.0 / 32.6 -- hence the window.  Not with PID: its integrator state sits in global memory
+    //    and an extra triple moves from SM to SM between chunks (L1 is not coherent).
+    // Both are bit-identical to the plain launch (tests/test_gpu_edges.py).  CCB_K1R_WINDOW (percent), CCB_K1R_WHOLE (0 / 1), CCB_K1R_NO_PERSIST,
+    // CCB_K1R_FORCE_PERSIST, CCB_K1R_CHUNKS: A/B knobs of the probes under tools/.
     static int nsm = 0;
     if (nsm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    // (the same with ONE warp per scheduler -- 2048 systems = 683 warps on 592 schedulers, the 2-GPU share of the bench batch -- does not pay:
-    // 24.4 ms against 24.1 ms plain; nothing pins four one-warp CTAs of an SM to four different schedulers)
-    int slots2 = 8 * nsm;
-    if (!(grid > slots2 && (long long)grid * 10 <= (long long)slots2 * 12) && !getenv("CCB_K1R_FORCE_PERSIST")) slots2 = 0;
-    const bool persist = a.persist && !a.knot_input && a.steps >= 256 && slots2 > 0 && C.kind != CCB_CTRL_PID && !getenv("CCB_K1R_NO_PERSIST");
+    const int slots2 = 8 * nsm;
+    int window = 135, whole = 1;
+    if (const char* e = getenv("CCB_K1R_WINDOW")) window = atoi(e);
+    if (const char* e = getenv("CCB_K1R_WHOLE")) whole = atoi(e);
+    const bool eligible = a.persist && !a.knot_input && a.steps >= 256 && !getenv("CCB_K1R_NO_PERSIST");
+    const bool sliced = grid > slots2 && C.kind != CCB_CTRL_PID && ((long long)grid * 100 <= (long long)slots2 * window || getenv("CCB_K1R_FORCE_PERSIST"));
+    const bool fits = grid <= slots2 && (whole || getenv("CCB_K1R_FORCE_PERSIST"));
+    const bool persist = eligible && (sliced || fits);
     if (persist) {
-        const int want = std::max(1, std::min(32, a.steps / 32));          // 32 chunks of >= 32 steps: every worker gets 32 + 32 extra / slots +- 1 items
-        a.chunk_steps = (a.steps + want - 1) / want;
-        a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps;
-        CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(a.B + 2) * sizeof(int), stream));      // the whole buffer (ccb_api.cu: B + 2 ints)
-        grid = slots2;        // compiled for 248 registers, at most 8 one-warp CTAs (= 2 warps per scheduler) fit an SM; with fewer registers
-        if (K1R_PERSIST_MAXREG < 224) smem = std::max(smem, (size_t)26 * 1024);     // shared memory caps the residency at 8 instead
-        if (const char* e = getenv("CCB_K1R_CHUNKS")) { const int nc = std::max(1, atoi(e)); a.chunk_steps = (a.steps + nc - 1) / nc; a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps; }
+        if (sliced) {
+            const int want = std::max(1, std::min(32, a.steps / 32));      // 32 chunks of >= 32 steps: every worker gets 32 + 32 extra / slots +- 1 items
+            a.chunk_steps = (a.steps + want - 1) / want;
+            if (const char* e = getenv("CCB_K1R_CHUNKS")) { const int nc = std::max(1, atoi(e)); a.chunk_steps = (a.steps + nc - 1) / nc; }
+            a.nchunks = (a.steps + a.chunk_steps - 1) / a.chunk_steps;
+            grid = slots2;
+        } else {
+            a.chunk_steps = a.steps; a.nchunks = 1;                        // workers = triples, no extra items
+        }
+        if (sliced) CCB_CUDA(cudaMemsetAsync(a.persist, 0, (size_t)(a.B + 2) * sizeof(int), stream));      // the flags of the extra triples (ccb_api.cu: B + 2 ints)
+#ifndef K1R_NO_SMEM_CAP
+        if (K1R_PERSIST_MAXREG < 224) smem = std::max(smem, (size_t)26 * 1024);     // with fewer registers shared memory caps the residency at 8 per SM
+#endif
         if (getenv("CCB_K1R_DEBUG")) {
             int occ = -1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rollout_rows_kernel<2, true, true>, 32, smem);

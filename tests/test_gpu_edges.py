@@ -167,8 +167,8 @@ def test_record_pipeline_is_bit_identical_to_one_launch(cc, monkeypatch):
 
 
 def test_persistent_time_sliced_launch_is_bit_identical(cc, monkeypatch):
-    """K1r's persistent launch (a batch of 1184 < W < 1.3 x 1184 warps: two warps per SM sub-partition pull (chunk of steps, triple of systems)
-    work items) must give the bits of the plain launch: states, multipliers and accumulated Newton counts, for LQR (finite horizon ending
+    """K1r's persistent launch (a batch of 1184 < W <= 1.35 x 1184 warps: two warps per SM sub-partition work through (chunk of steps, triple of
+    systems) items on a static schedule) must give the bits of the plain launch: states, multipliers and accumulated Newton counts, for LQR (finite horizon ending
     inside the rollout), open-loop tables and the uncontrolled mechanism.  B = 3700 cartpoles -> 1234 warps."""
     mech, cfg = cc.examples.cartpole()
     B, steps = 3700, 272                                         # chunks of 17 steps, the last one ragged
@@ -191,6 +191,45 @@ def test_persistent_time_sliced_launch_is_bit_identical(cc, monkeypatch):
             res.append((fin, lam, status))
         out[mode] = res
     for a, b in zip(out["plain"], out["persistent"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.all(a[2] > 0)
+
+
+def test_whole_batch_launch_on_the_spill_free_instantiation_is_bit_identical(cc, monkeypatch):
+    """batches of at most two warps per scheduler run K1r's 255-register instantiation in one chunk (no time slicing): the bits of the plain
+    168-register kernel for LQR, open-loop tables, no controller and PID (whose integrator state lives on the device)"""
+    mech, cfg = cc.examples.cartpole()
+    B, steps = 901, 300
+    st0 = cartpole_states(cc, mech, B, seed=12)
+    lqr = cc.LQR(mech, cc.getid(mech.bodies), cfg["eqcids"], cfg["Q"], cfg["R"], 2.0, xd=cfg["xd"])
+    U = 0.3 * np.sin(np.arange(steps)[:, None] * 0.05)
+    dp, dcfg = cc.examples.doublependulum()
+    Bp = 77
+    goals = np.stack([np.linspace(-2.0, 2.0, Bp), np.linspace(1.5, -1.5, Bp)], axis=1)
+    out = {}
+    for mode in ("plain", "whole"):
+        if mode == "plain":
+            monkeypatch.setenv("CCB_K1R_NO_PERSIST", "1")
+        else:
+            monkeypatch.delenv("CCB_K1R_NO_PERSIST")
+        res = []
+        for ctrl in (lqr, cc.OpenLoop(mech, cfg["eqcids"], U), None):
+            batch = cc.Batch(mech, B)
+            batch.set_state(st0)
+            _, status = batch.simulate(ctrl, 1, steps)
+            fin, lam = batch.get_state(want_lambda=True)
+            res.append((fin, lam, status))
+        pid = cc.PID(dp, dcfg["eqcids"], goals, P=dcfg["P"], I=dcfg["I"], D=dcfg["D"])
+        batch = cc.Batch(dp, Bp)
+        batch.set_state(dp.batch_states(Bp))
+        _, status = batch.simulate(pid, 1, steps)
+        _, status2 = batch.simulate(pid, steps + 1, 40)               # a short second call (plain kernel in both modes) continues from the PID state
+        fin, lam = batch.get_state(want_lambda=True)
+        gi, gl = pid.pid_state(Bp)
+        res.append((fin, lam, status, status2, gi, gl))
+        out[mode] = res
+    for a, b in zip(out["plain"], out["whole"]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
         assert np.all(a[2] > 0)
