@@ -196,6 +196,26 @@ def test_persistent_time_sliced_launch_is_bit_identical(cc, monkeypatch):
         assert np.all(a[2] > 0)
 
 
+@pytest.mark.parametrize("B", [3552, 3553, 4794, 4795])
+def test_launch_selection_edges_against_the_oracle(cc, orc, B):
+    """the batch sizes at which K1r's launcher changes route on a 148-SM device -- 3552 cartpoles = 1184 warps (whole batch on the 255-register
+    instantiation), 3553 (time-sliced, ONE extra triple), 4794 (time-sliced, the last batch inside the 1.35x window: 414 extra triples),
+    4795 (plain launch) -- each against the oracle: states, multiplier-free failure flags and Newton totals of every system"""
+    mech, cfg = cc.examples.cartpole()
+    steps = 260                                                   # >= 256: the persistent routes are eligible; chunks of 33 steps, the last ragged
+    o = oracle_lqr_gains(cc, orc, mech, cfg, horizon=2.0)          # N = 200 < steps: the k < N gate closes inside a chunk
+    st0 = cartpole_states(cc, mech, B, seed=13)
+    ctrl_o = o["om"].make_ctrl(B, kind="lqr_finite", eqc=o["eqc_idx"], N=o["N"], K=o["K"], zd=o["zd"], Fd=o["Fd"])
+    ref = o["om"].simulate(st0, steps, ctrl=ctrl_o, nthreads=8, eps=1e-7)
+    lqr = cc.LQR.from_gains(mech, cfg["eqcids"], o["K"], o["N"], xd=cfg["xd"])
+    batch = cc.Batch(mech, B)
+    batch.set_state(st0)
+    _, status = batch.simulate(lqr, 1, steps, eps=1e-7)
+    assert np.all(status > 0) and np.all(ref["iters"] > 0)
+    assert rel_err(batch.get_state(), ref["states"]) < 1e-9
+    assert np.array_equal(status, ref["iters"])                   # at eps = 1e-7 the iteration count is a well-defined integer (DESIGN "Integer outputs")
+
+
 def test_whole_batch_launch_on_the_spill_free_instantiation_is_bit_identical(cc, monkeypatch):
     """batches of at most two warps per scheduler run K1r's 255-register instantiation in one chunk (no time slicing): the bits of the plain
     168-register kernel for LQR, open-loop tables, no controller and PID (whose integrator state lives on the device)"""
