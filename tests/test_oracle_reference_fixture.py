@@ -118,3 +118,10 @@ def test_deltabot_gravity_compensation_constant(cc, orc):
     assert np.abs(_deltabot_velocity_after_one_step(om, st0, eqc, u)).max() < 1e-11
     assert abs(u[0] + u[1]) < 1e-9                                                                  # mirror symmetry of the two legs
     assert abs(u[0] - 6.7879484) < 1e-7 and int(u[0] * 1e7) == 67879484                             # 6.78794845...: every printed digit
+    # the third leg: statics by virtual work, independent of both programs.  Symmetric vertical motion of the platform (legs at a = b = 45 degrees
+    # from the vertical, lower leg 1 m / 1 kg, upper leg 0.5 m / 0.5 kg, platform sqrt(2)/2 kg): U = g [(m_l + 2 m_u + m_p) cos a + (m_u / 2 + m_p / 2)
+    # cos b], loop closure sin a - sin b / 2 = const gives da = db / 2, the two actuated joint angles change by -+ db: 2 tau = |dU / db|
+    m_l, m_u, m_p, g = 1.0, 0.5, math.sqrt(2) / 2, 9.81
+    tau = g * math.sin(math.pi / 4) * ((m_l + 2 * m_u + m_p) / 2 + (m_u + m_p) / 2) / 2
+    assert abs(tau - 6.7879484) < 6e-8                      # the reference's literal is this number cut after eight digits
+    assert abs(u[0] - tau) < 1e-9                           # and the restated step map has exactly this equilibrium
